@@ -1,0 +1,139 @@
+/* mbpol_b200.h -- C ABI of the B200-native MB-pol 2B+3B short-range many-body path.
+ *
+ * This is the drop-in boundary: everything a platform kernel of the reference plugin does for
+ *   CalcMBPolTwoBodyForceKernel   (openmmapi/include/openmm/mbpolKernels.h:134-168)
+ *   CalcMBPolThreeBodyForceKernel (openmmapi/include/openmm/mbpolKernels.h:173-207)
+ * i.e. what ReferenceCalcMBPol{Two,Three}BodyForceKernel::initialize/execute/copyParametersToContext do
+ * (platforms/reference/src/MBPolReferenceKernels.cpp:341-410, 430-497) and what the to-be-replaced
+ * CudaCalcMBPol{Two,Three}BodyForceKernel do (platforms/cuda/src/CudaMBPolKernels.cpp:174-304, 1722-2005),
+ * is reachable through the plain-C entry points below.  No C++ / torch / OpenMM types cross this boundary: plain
+ * pointers, sizes and a CUDA stream handle passed as void*.  Every function returns 0 on success or a negative
+ * MBPOL_E* code; mbpol_last_error(ctx) gives the message (the C++ adapter turns it into OpenMM::OpenMMException).
+ *
+ * Units follow OpenMM: positions / box / cutoffs in nm, energies in kJ/mol, forces in kJ/mol/nm.
+ * One context per OpenMM Context; a context is not re-entrant.
+ */
+#ifndef MBPOL_B200_H
+#define MBPOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBPOL_ABI_VERSION 1
+
+/* error codes */
+#define MBPOL_OK            0
+#define MBPOL_EINVAL       (-1)   /* bad argument */
+#define MBPOL_ECUDA        (-2)   /* CUDA runtime / driver error */
+#define MBPOL_EBOX         (-3)   /* periodic box smaller than twice the cutoff (MBPolReferenceKernels.cpp:384-391) */
+#define MBPOL_ECHANGED     (-4)   /* number of molecules changed (MBPolReferenceKernels.cpp:402-403) */
+#define MBPOL_ENOMEM       (-5)
+
+/* nonbonded method: values of MBPolTwoBodyForce::NonbondedMethod (openmmapi/include/openmm/MBPolTwoBodyForce.h:62-74) */
+#define MBPOL_NOCUTOFF            0   /* treated as CutoffNonPeriodic with an infinite cutoff */
+#define MBPOL_CUTOFF_PERIODIC     1
+#define MBPOL_CUTOFF_NONPERIODIC  2
+
+/* mbpol_eval flags */
+#define MBPOL_DO_2B        1u     /* evaluate the MBPolTwoBodyForce term   */
+#define MBPOL_DO_3B        2u     /* evaluate the MBPolThreeBodyForce term */
+#define MBPOL_KEEP_LISTS   4u     /* reuse the tuple lists of the previous call (default: rebuild, like the reference) */
+
+typedef struct mbpol_ctx mbpol_ctx;
+
+/* What MBPol{Two,Three}BodyForce carry (MBPolTwoBodyForce.h:57-166): per-molecule particle indices {O,H1,H2},
+ * a cutoff and a nonbonded method each.  The PIP coefficients and nonlinear parameters are baked into the library
+ * (they are compile-time constants in the reference too, mbpol_2body_constants.h:33). */
+typedef struct mbpol_config {
+    int32_t        abi_version;      /* MBPOL_ABI_VERSION */
+    int32_t        n_molecules;      /* number of addParticle() calls */
+    int32_t        n_particles;      /* length of the position / force arrays (>= 3*n_molecules; M sites are skipped) */
+    const int32_t* particle_indices; /* n_molecules x 3 global indices {O,H1,H2}, copied */
+    double         cutoff_2b_nm;     /* mbpol.xml: 0.65 */
+    double         cutoff_3b_nm;     /* mbpol.xml: 0.45 */
+    int32_t        method_2b;        /* MBPOL_NOCUTOFF | MBPOL_CUTOFF_PERIODIC | MBPOL_CUTOFF_NONPERIODIC */
+    int32_t        method_3b;
+    int32_t        device;           /* CUDA device ordinal, -1 = current device */
+    int32_t        reserved;
+} mbpol_config;
+
+/* counters of the last mbpol_eval call */
+typedef struct mbpol_stats {
+    int64_t n_pairs;        /* listed dimers  (O-O <= cutoff_2b)                        */
+    int64_t n_triplets;     /* listed trimers (reference chain set)    */
+    int64_t n_pairs_owned;  /* dimers / trimers evaluated by THIS context (owner range)  */
+    int64_t n_triplets_owned;
+    float   ms_lists, ms_2b, ms_3b, ms_reduce;   /* device time of the stages (CUDA events), 0 if timing disabled */
+} mbpol_stats;
+
+/* replaces CalcMBPol*ForceKernel::initialize (MBPolReferenceKernels.cpp:341-360, 430-449) */
+int  mbpol_create(mbpol_ctx** out, const mbpol_config* cfg);
+void mbpol_destroy(mbpol_ctx* ctx);
+const char* mbpol_last_error(const mbpol_ctx* ctx);     /* ctx may be NULL: error of the last failed mbpol_create */
+
+/* replaces CalcMBPol*ForceKernel::copyParametersToContext (MBPolReferenceKernels.cpp:401-415, 485-497):
+ * new particle indices for the same number of molecules; MBPOL_ECHANGED if the count differs */
+int  mbpol_update_particles(mbpol_ctx* ctx, int32_t n_molecules, const int32_t* particle_indices);
+
+/* rectangular periodic box edge lengths (extractBoxSize, MBPolReferenceKernels.cpp:63-66) */
+int  mbpol_set_box(mbpol_ctx* ctx, const double box_nm[3]);
+
+/* multi-GPU owner-molecule partition: this context evaluates only the tuples whose owner (highest molecule index I)
+ * falls in slice `rank` of `world` slices balanced by 30,601*dimers + 111,818*trimers per owner.
+ * world = 1 (default) evaluates everything.  Forces / energies returned are then partial sums to be all-reduced. */
+int  mbpol_set_partition(mbpol_ctx* ctx, int32_t rank, int32_t world);
+
+/* replaces CalcMBPol{Two,Three}BodyForceKernel::execute (MBPolReferenceKernels.cpp:362-399, 451-483).
+ *   pos_nm : DEVICE pointer, n_particles x 3 doubles
+ *   force  : DEVICE pointer, n_particles x 3 doubles, the path ADDS its forces (like the reference); may be NULL
+ *   energy : HOST pointer to 2 doubles {E_2B, E_3B} in kJ/mol; may be NULL (no device->host sync is then made)
+ *   stream : cudaStream_t / CUstream as void*; NULL = legacy default stream */
+int  mbpol_eval(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, uint32_t flags, void* stream);
+
+/* same call with HOST buffers: copies positions in, forces out (force is ADDED into), synchronous.
+ * This is the entry the Reference-platform-style adapter and the end-to-end benchmark use. */
+int  mbpol_eval_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, uint32_t flags);
+
+/* OpenMM CUDA force-buffer convention (platforms/cuda/src/kernels/twobodyForce.cu:442-457): int64 fixed point,
+ * value * 2^32, SoA [x: padded][y: padded][z: padded].  Adds the forces of the last mbpol_eval (which must have been
+ * called with force == NULL or not) into omm_force for the particles of this context. DEVICE pointer. */
+int  mbpol_add_forces_fixed_point(mbpol_ctx* ctx, long long* omm_force, int32_t padded_num_atoms, void* stream);
+
+/* tuple lists of the last evaluation in canonical order (ascending I, then J[, then K]; I > J > K), for bit-exact
+ * comparison with computeNeighborListVoxelHash / computeThreeNeighborListVoxelHash
+ * (platforms/reference/src/ReferenceThreeNeighborList.cpp:181-226).  HOST pointers.  Call with out == NULL to get *n. */
+int  mbpol_get_pairs(mbpol_ctx* ctx, int32_t* out /* n x 2 */, size_t* n);
+int  mbpol_get_triplets(mbpol_ctx* ctx, int32_t* out /* n x 3 */, size_t* n);
+
+int  mbpol_get_stats(const mbpol_ctx* ctx, mbpol_stats* out);
+int  mbpol_set_timing(mbpol_ctx* ctx, int32_t enabled);   /* record per-stage CUDA events (adds a sync per eval) */
+
+/* ---- lower-level entry points used by the unit tests and the roofline benchmark ------------------------------- */
+
+/* evaluate the bare PIP (poly_2b_v6x_eval: poly-2b-v6x.cpp:3 / poly_3b_v2x::eval: poly-3b-v2x.cpp:3) on n tuples.
+ *   order : 2 or 3;  x : DEVICE [n_vars][ld] (31 or 36 variables, tuple index fastest)
+ *   out   : DEVICE [1+n_vars][ld]: row 0 = E_poly (kcal/mol), rows 1.. = dE/dx */
+int  mbpol_pip_eval(int order, const double* x, double* out, int64_t n, int64_t ld, void* stream);
+
+/* per-tuple energies (kJ/mol) and force blocks (kJ/mol/nm; 6x3 / 9x3 per tuple in slot order Oa,Ha1,Ha2,Ob,...)
+ * for explicit tuple lists over stride-3 molecules (pos = n_mol x 3 x 3).  All pointers DEVICE. */
+int  mbpol_eval_tuples(int order, const double* pos_nm, int32_t n_mol, const int32_t* tuples, int64_t n_tuples,
+                       const double box_nm[3], int periodic, double* e_each, double* f_each, void* stream);
+
+/* register-resident DFMA loop: measures the FP64 FMA-pipe peak of the device this library runs on.
+ * Returns achieved TFLOP/s in *tflops. */
+int  mbpol_measure_fp64_peak(double* tflops, double* ms);
+
+/* constants of the work model */
+#define MBPOL_FLOP_PER_DIMER   30601   /* 10,707 mul + 19,894 add, poly-2b-v6x.cpp */
+#define MBPOL_FLOP_PER_TRIMER  111818  /* 22,294 mul + 89,524 add, poly-3b-v2x.cpp */
+int  mbpol_pip_instruction_count(int order);   /* FP64 instructions our evaluator issues per tuple */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBPOL_B200_H */

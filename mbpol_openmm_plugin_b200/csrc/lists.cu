@@ -1,0 +1,525 @@
+// GPU cell list and tuple enumeration: oxygens -> sorted neighbour rows -> compacted, canonically ordered
+// pair list (I > J) and chain-triplet list (I > J > K), plus the tuple->molecule contribution index used by the
+// deterministic force reduction.
+//
+// Set semantics reproduced bit-exactly:
+//   pairs     {(I,J) : I > J, d2(I,J) <= c2^2}                       OpenMM computeNeighborListVoxelHash as called at
+//                                                                    platforms/reference/src/MBPolReferenceKernels.cpp:380-382
+//   triplets  {(I,J,K) : J in nearby[I], K in nearby[J]},  nearby[i] = {j < i : d2(i,j) <= c3^2}
+//                                                                    platforms/reference/src/ReferenceThreeNeighborList.cpp:181-226
+//   d2 uses periodicDifference / compPairDistanceSquared verbatim in rounding behaviour (:14-33): every operation is
+//   issued through a round-to-nearest intrinsic so no FMA contraction can flip a borderline `<=` decision.
+// Emission order is canonical (ascending I, then J, then K); the reference's own order is voxel-scan dependent and is
+// compared after sorting.
+#include <cub/cub.cuh>
+
+#include "lists.h"
+
+namespace mbpol {
+
+namespace {
+
+__device__ __forceinline__ double periodic_difference(double v1, double v2, double period) {
+    const double diff = __dsub_rn(v1, v2);
+    const double base = __dmul_rn(floor(__dadd_rn(__ddiv_rn(diff, period), 0.5)), period);
+    return __dsub_rn(diff, base);
+}
+
+// squared distance "from pos1 to pos2" exactly as the reference evaluates it with pos1 = higher index
+__device__ __forceinline__ double pair_d2(const double* __restrict__ p1, const double* __restrict__ p2, const GridArg& g) {
+    double dx, dy, dz;
+    if (!g.periodic) {
+        dx = __dsub_rn(p2[0], p1[0]);
+        dy = __dsub_rn(p2[1], p1[1]);
+        dz = __dsub_rn(p2[2], p1[2]);
+    } else {
+        dx = periodic_difference(p2[0], p1[0], g.box[0]);
+        dy = periodic_difference(p2[1], p1[1], g.box[1]);
+        dz = periodic_difference(p2[2], p1[2], g.box[2]);
+    }
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int cell_coord(double x, int d, const GridArg& g) {
+    double f;
+    if (g.periodic) {
+        f = x / g.box[d];
+        f -= floor(f);
+    } else {
+        f = (x - g.lo[d]) * g.inv_extent[d];
+    }
+    int c = (int)(f * g.nc[d]);
+    return min(max(c, 0), g.nc[d] - 1);
+}
+
+__global__ void gather_oxygens_kernel(const double* __restrict__ pos, const int32_t* __restrict__ idx, int n,
+                                      double* __restrict__ posO) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const double* p = pos + 3 * (size_t)idx[3 * m];
+    posO[3 * m] = p[0];
+    posO[3 * m + 1] = p[1];
+    posO[3 * m + 2] = p[2];
+}
+
+// single-block bounding box (non-periodic systems are small clusters)
+__global__ void bbox_kernel(const double* __restrict__ posO, int n, double* __restrict__ out /*lo[3],hi[3]*/) {
+    __shared__ double slo[3][256], shi[3][256];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int m = threadIdx.x; m < n; m += blockDim.x)
+        for (int d = 0; d < 3; ++d) {
+            lo[d] = fmin(lo[d], posO[3 * m + d]);
+            hi[d] = fmax(hi[d], posO[3 * m + d]);
+        }
+    for (int d = 0; d < 3; ++d) {
+        slo[d][threadIdx.x] = lo[d];
+        shi[d][threadIdx.x] = hi[d];
+    }
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int d = 0; d < 3; ++d) {
+                slo[d][threadIdx.x] = fmin(slo[d][threadIdx.x], slo[d][threadIdx.x + s]);
+                shi[d][threadIdx.x] = fmax(shi[d][threadIdx.x], shi[d][threadIdx.x + s]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int d = 0; d < 3; ++d) {
+            out[d] = slo[d][0];
+            out[3 + d] = shi[d][0];
+        }
+}
+
+__global__ void cell_count_kernel(const double* __restrict__ posO, int n, GridArg g, int* __restrict__ cell_of,
+                                  int* __restrict__ cell_count) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int cx = cell_coord(posO[3 * m], 0, g), cy = cell_coord(posO[3 * m + 1], 1, g),
+              cz = cell_coord(posO[3 * m + 2], 2, g);
+    const int c = (cx * g.nc[1] + cy) * g.nc[2] + cz;
+    cell_of[m] = c;
+    atomicAdd(cell_count + c, 1);      // integer counts: the result does not depend on arrival order
+}
+
+__global__ void cell_fill_kernel(int n, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
+                                 int* __restrict__ cell_cursor, int* __restrict__ cell_members) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int c = cell_of[m];
+    // order inside a cell is arrival order; every consumer sorts its neighbour row by index afterwards
+    cell_members[cell_start[c] + atomicAdd(cell_cursor + c, 1)] = m;
+}
+
+// Visit all j != i in the 27 (or fewer, for tiny grids) cells around i.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(int i, const double* __restrict__ posO, const GridArg& g,
+                                                   const int* __restrict__ cell_start,
+                                                   const int* __restrict__ cell_members, F&& f) {
+    int c[3], lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c[d] = cell_coord(posO[3 * i + d], d, g);
+        if (g.periodic) {
+            if (g.nc[d] >= 3) { lo[d] = c[d] - 1; hi[d] = c[d] + 1; }
+            else { lo[d] = 0; hi[d] = g.nc[d] - 1; }          // 1 or 2 cells: visit each exactly once
+        } else {
+            lo[d] = max(c[d] - 1, 0);
+            hi[d] = min(c[d] + 1, g.nc[d] - 1);
+        }
+    }
+    for (int x = lo[0]; x <= hi[0]; ++x) {
+        const int wx = (x + g.nc[0]) % g.nc[0];
+        for (int y = lo[1]; y <= hi[1]; ++y) {
+            const int wy = (y + g.nc[1]) % g.nc[1];
+            for (int z = lo[2]; z <= hi[2]; ++z) {
+                const int wz = (z + g.nc[2]) % g.nc[2];
+                const int cell = (wx * g.nc[1] + wy) * g.nc[2] + wz;
+                for (int k = cell_start[cell]; k < cell_start[cell + 1]; ++k) {
+                    const int j = cell_members[k];
+                    if (j != i) f(j);
+                }
+            }
+        }
+    }
+}
+
+// pass 1: number of neighbours within c2 / c3 (full rows: both j < i and j > i)
+__global__ void row_count_kernel(const double* __restrict__ posO, int n, GridArg g, const int* __restrict__ cell_start,
+                                 const int* __restrict__ cell_members, double c2sq, double c3sq,
+                                 int* __restrict__ cnt2, int* __restrict__ cnt3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int n2 = 0, n3 = 0;
+    for_each_candidate(i, posO, g, cell_start, cell_members, [&](int j) {
+        const int hi = max(i, j), lo = min(i, j);
+        const double d2 = pair_d2(posO + 3 * hi, posO + 3 * lo, g);
+        n2 += (d2 <= c2sq);
+        n3 += (d2 <= c3sq);
+    });
+    cnt2[i] = n2;
+    cnt3[i] = n3;
+}
+
+__device__ __forceinline__ int sort_row(int* __restrict__ row, int len, int self) {
+    for (int a = 1; a < len; ++a) {          // rows are short (tens of entries): insertion sort in place
+        const int v = row[a];
+        int b = a - 1;
+        while (b >= 0 && row[b] > v) {
+            row[b + 1] = row[b];
+            --b;
+        }
+        row[b + 1] = v;
+    }
+    int lower = 0;
+    while (lower < len && row[lower] < self) ++lower;
+    return lower;
+}
+
+// pass 2: fill + sort the rows, record how many entries are lower-index ("nearby" in the reference's words)
+__global__ void row_fill_kernel(const double* __restrict__ posO, int n, GridArg g, const int* __restrict__ cell_start,
+                                const int* __restrict__ cell_members, double c2sq, double c3sq,
+                                const int64_t* __restrict__ ro2, const int64_t* __restrict__ ro3,
+                                int* __restrict__ nbr2, int* __restrict__ nbr3, int* __restrict__ low2,
+                                int* __restrict__ low3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int* r2 = nbr2 + ro2[i];
+    int* r3 = nbr3 + ro3[i];
+    int n2 = 0, n3 = 0;
+    for_each_candidate(i, posO, g, cell_start, cell_members, [&](int j) {
+        const int hi = max(i, j), lo = min(i, j);
+        const double d2 = pair_d2(posO + 3 * hi, posO + 3 * lo, g);
+        if (d2 <= c2sq) r2[n2++] = j;
+        if (d2 <= c3sq) r3[n3++] = j;
+    });
+    low2[i] = sort_row(r2, n2, i);
+    low3[i] = sort_row(r3, n3, i);
+}
+
+// pairs[p] = (I, J) for J in the lower part of I's row; p = pstart[I] + rank
+__global__ void emit_pairs_kernel(int n, const int64_t* __restrict__ ro, const int* __restrict__ nbr,
+                                  const int* __restrict__ low, const int64_t* __restrict__ pstart,
+                                  int32_t* __restrict__ pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int* row = nbr + ro[i];
+    int32_t* out = pairs + 2 * pstart[i];
+    for (int k = 0; k < low[i]; ++k) {
+        out[2 * k] = i;
+        out[2 * k + 1] = row[k];
+    }
+}
+
+// number of triplets hanging off each (I,J) pair of the 3B pair list = |nearby[J]|
+__global__ void triplet_count_kernel(int64_t nq, const int32_t* __restrict__ qpairs, const int* __restrict__ low3,
+                                     int* __restrict__ cnt) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    cnt[q] = low3[qpairs[2 * q + 1]];
+}
+
+__global__ void emit_triplets_kernel(int64_t nq, const int32_t* __restrict__ qpairs, const int64_t* __restrict__ ro3,
+                                     const int* __restrict__ nbr3, const int* __restrict__ low3,
+                                     const int64_t* __restrict__ tstart, int32_t* __restrict__ trips) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int I = qpairs[2 * q], J = qpairs[2 * q + 1];
+    const int* row = nbr3 + ro3[J];
+    int32_t* out = trips + 3 * tstart[q];
+    for (int k = 0; k < low3[J]; ++k) {
+        out[3 * k] = I;
+        out[3 * k + 1] = J;
+        out[3 * k + 2] = row[k];
+    }
+}
+
+// cumulative work W(I) = 30601 * pairs owned by molecules < I + 111818 * triplets owned by molecules < I
+__global__ void owner_weight_kernel(int n, const int64_t* __restrict__ pstart, const int64_t* __restrict__ qstart,
+                                    const int64_t* __restrict__ tstart, int has2, int has3, int64_t* __restrict__ W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t w = 0;
+    if (has2) w += (int64_t)MBPOL_FLOP_PER_DIMER * pstart[i];
+    if (has3) w += (int64_t)MBPOL_FLOP_PER_TRIMER * tstart[qstart[i]];
+    W[i] = w;
+}
+
+__global__ void contribution_keys_kernel(int64_t first, int64_t count, int width, const int32_t* __restrict__ tuples,
+                                         int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= count * width) return;
+    const int64_t t = e / width;
+    const int r = (int)(e - t * width);
+    keys[e] = tuples[width * (first + t) + r];
+    vals[e] = (int32_t)e;                       // (local tuple index) * width + role
+}
+
+__global__ void segment_offsets_kernel(int n, int64_t count, const int32_t* __restrict__ sorted_keys,
+                                       int64_t* __restrict__ off) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > n) return;
+    int64_t lo = 0, hi = count;                 // lower_bound(m)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < m) lo = mid + 1; else hi = mid;
+    }
+    off[m] = lo;
+}
+
+inline unsigned blocks(int64_t n, int b = 128) { return (unsigned)((n + b - 1) / b); }
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return MBPOL_ECUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+}  // namespace
+
+int DeviceBuf::reserve(size_t bytes, std::string& err) {
+    if (bytes <= cap) return MBPOL_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&ptr, want) != cudaSuccess) {
+        cudaGetLastError();
+        err = "cudaMalloc of " + std::to_string(want) + " bytes failed";
+        return MBPOL_ENOMEM;
+    }
+    cap = want;
+    return MBPOL_OK;
+}
+DeviceBuf::~DeviceBuf() {
+    if (ptr) cudaFree(ptr);
+}
+
+struct ToInt64 {
+    __host__ __device__ int64_t operator()(int v) const { return (int64_t)v; }
+};
+
+static int exclusive_scan(const int* in, int64_t* out, int64_t n, DeviceBuf& tmp, cudaStream_t s, std::string& err) {
+    // out[0..n] (n+1 entries): out[n] = total (in[n] must be 0).  Input is widened to int64 on the fly.
+    cub::TransformInputIterator<int64_t, ToInt64, const int*> it(in, ToInt64());
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, n + 1, s));
+    int rc = tmp.reserve(bytes, err);
+    if (rc) return rc;
+    CK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, it, out, n + 1, s));
+    return MBPOL_OK;
+}
+
+int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const double box[3], bool periodic,
+                      double cut2, double cut3, bool want2, bool want3, cudaStream_t s, std::string& err) {
+    n = n_mol;
+    n_pairs = n_trips = n_qpairs = 0;
+    has2 = want2;
+    has3 = want3;
+    if (n <= 0 || (!want2 && !want3)) return MBPOL_OK;
+    int rc;
+#define RES(buf, count, type) if ((rc = buf.reserve(sizeof(type) * (size_t)(count), err))) return rc
+    RES(posO, 3 * n, double);
+    gather_oxygens_kernel<<<blocks(n), 128, 0, s>>>(pos, idx, n, posO.as<double>());
+
+    // ---- grid ---------------------------------------------------------------------------------------------------
+    // rows are only needed out to the largest finite cutoff in use; "no cutoff" (1e10) degenerates to one cell
+    const double rc_max = fmax(want2 ? cut2 : 0.0, want3 ? cut3 : 0.0) * (1.0 + 1e-6);
+    GridArg g;
+    g.periodic = periodic ? 1 : 0;
+    double extent[3];
+    if (periodic) {
+        for (int d = 0; d < 3; ++d) {
+            g.box[d] = box[d];
+            g.lo[d] = 0.0;
+            extent[d] = box[d];
+        }
+    } else {
+        RES(scratch, 6, double);
+        bbox_kernel<<<1, 256, 0, s>>>(posO.as<double>(), n, scratch.as<double>());
+        double bb[6];
+        CK(cudaMemcpyAsync(bb, scratch.ptr, sizeof bb, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int d = 0; d < 3; ++d) {
+            g.box[d] = 0.0;
+            g.lo[d] = bb[d];
+            extent[d] = fmax(bb[3 + d] - bb[d], 1e-9) * (1.0 + 1e-9);
+        }
+    }
+    int64_t ncell = 1;
+    for (int d = 0; d < 3; ++d) {
+        double q = floor(extent[d] / rc_max);
+        g.nc[d] = (int)fmin(fmax(q, 1.0), 1024.0);
+        ncell *= g.nc[d];
+    }
+    while (ncell > 8LL * n + 64) {             // sparse system: coarsen, keeps cell edge >= cutoff
+        int d = g.nc[0] >= g.nc[1] && g.nc[0] >= g.nc[2] ? 0 : (g.nc[1] >= g.nc[2] ? 1 : 2);
+        ncell /= g.nc[d];
+        g.nc[d] = (g.nc[d] + 1) / 2;
+        ncell *= g.nc[d];
+    }
+    for (int d = 0; d < 3; ++d) g.inv_extent[d] = 1.0 / extent[d];
+
+    // ---- cells --------------------------------------------------------------------------------------------------
+    RES(cell_of, n, int);
+    RES(cell_count, ncell + 1, int);
+    RES(cell_start64, ncell + 1, int64_t);
+    RES(cell_start, ncell + 1, int);
+    RES(cell_cursor, ncell, int);
+    RES(cell_members, n, int);
+    CK(cudaMemsetAsync(cell_count.ptr, 0, sizeof(int) * (ncell + 1), s));
+    CK(cudaMemsetAsync(cell_cursor.ptr, 0, sizeof(int) * ncell, s));
+    cell_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_of.as<int>(), cell_count.as<int>());
+    {
+        size_t bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cell_count.as<int>(), cell_start.as<int>(), (int)ncell + 1, s));
+        if ((rc = cub_tmp.reserve(bytes, err))) return rc;
+        CK(cub::DeviceScan::ExclusiveSum(cub_tmp.ptr, bytes, cell_count.as<int>(), cell_start.as<int>(), (int)ncell + 1, s));
+    }
+    cell_fill_kernel<<<blocks(n), 128, 0, s>>>(n, cell_of.as<int>(), cell_start.as<int>(), cell_cursor.as<int>(),
+                                               cell_members.as<int>());
+
+    // ---- neighbour rows -----------------------------------------------------------------------------------------
+    const double c2sq = want2 ? cut2 * cut2 : -1.0, c3sq = want3 ? cut3 * cut3 : -1.0;
+    RES(cnt2, n + 1, int);
+    RES(cnt3, n + 1, int);
+    RES(ro2, n + 1, int64_t);
+    RES(ro3, n + 1, int64_t);
+    RES(low2, n + 1, int);
+    RES(low3, n + 1, int);
+    CK(cudaMemsetAsync(cnt2.ptr, 0, sizeof(int) * (n + 1), s));
+    CK(cudaMemsetAsync(cnt3.ptr, 0, sizeof(int) * (n + 1), s));
+    CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
+    CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
+    row_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
+                                               c2sq, c3sq, cnt2.as<int>(), cnt3.as<int>());
+    if ((rc = exclusive_scan(cnt2.as<int>(), ro2.as<int64_t>(), n, cub_tmp, s, err))) return rc;
+    if ((rc = exclusive_scan(cnt3.as<int>(), ro3.as<int64_t>(), n, cub_tmp, s, err))) return rc;
+    int64_t tot[2];
+    CK(cudaMemcpyAsync(&tot[0], ro2.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tot[1], ro3.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    RES(nbr2, tot[0] + 1, int);
+    RES(nbr3, tot[1] + 1, int);
+    row_fill_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
+                                              c2sq, c3sq, ro2.as<int64_t>(), ro3.as<int64_t>(), nbr2.as<int>(),
+                                              nbr3.as<int>(), low2.as<int>(), low3.as<int>());
+
+    // ---- pair lists (2B pairs, 3B hub pairs) ----------------------------------------------------------------------
+    RES(pstart, n + 1, int64_t);
+    RES(qstart, n + 1, int64_t);
+    if ((rc = exclusive_scan(low2.as<int>(), pstart.as<int64_t>(), n, cub_tmp, s, err))) return rc;
+    if ((rc = exclusive_scan(low3.as<int>(), qstart.as<int64_t>(), n, cub_tmp, s, err))) return rc;
+    CK(cudaMemcpyAsync(&tot[0], pstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tot[1], qstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_pairs = tot[0];
+    n_qpairs = tot[1];
+    RES(pairs, 2 * n_pairs + 2, int32_t);
+    RES(qpairs, 2 * n_qpairs + 2, int32_t);
+    emit_pairs_kernel<<<blocks(n), 128, 0, s>>>(n, ro2.as<int64_t>(), nbr2.as<int>(), low2.as<int>(),
+                                                pstart.as<int64_t>(), pairs.as<int32_t>());
+    emit_pairs_kernel<<<blocks(n), 128, 0, s>>>(n, ro3.as<int64_t>(), nbr3.as<int>(), low3.as<int>(),
+                                                qstart.as<int64_t>(), qpairs.as<int32_t>());
+
+    // ---- triplets -------------------------------------------------------------------------------------------------
+    RES(tcnt, n_qpairs + 1, int);
+    RES(tstart, n_qpairs + 1, int64_t);
+    CK(cudaMemsetAsync(tcnt.ptr, 0, sizeof(int) * (n_qpairs + 1), s));
+    if (n_qpairs > 0)
+        triplet_count_kernel<<<blocks(n_qpairs), 128, 0, s>>>(n_qpairs, qpairs.as<int32_t>(), low3.as<int>(),
+                                                              tcnt.as<int>());
+    if ((rc = exclusive_scan(tcnt.as<int>(), tstart.as<int64_t>(), n_qpairs, cub_tmp, s, err))) return rc;
+    CK(cudaMemcpyAsync(&tot[0], tstart.as<int64_t>() + n_qpairs, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_trips = tot[0];
+    RES(trips, 3 * n_trips + 3, int32_t);
+    if (n_qpairs > 0)
+        emit_triplets_kernel<<<blocks(n_qpairs), 128, 0, s>>>(n_qpairs, qpairs.as<int32_t>(), ro3.as<int64_t>(),
+                                                              nbr3.as<int>(), low3.as<int>(), tstart.as<int64_t>(),
+                                                              trips.as<int32_t>());
+    // ---- cumulative owner weights for the multi-GPU partition -------------------------------------------------------
+    RES(weight, n + 1, int64_t);
+    owner_weight_kernel<<<blocks(n + 1), 128, 0, s>>>(n, pstart.as<int64_t>(), qstart.as<int64_t>(),
+                                                      tstart.as<int64_t>(), want2, want3, weight.as<int64_t>());
+    CK(cudaGetLastError());
+#undef RES
+    return MBPOL_OK;
+}
+
+int TupleLists::partition(int rank, int world, cudaStream_t s, std::string& err) {
+    // Owner ranges [I0, I1) with equal cumulative work; every rank computes the same boundaries from the same lists.
+    own_p0 = own_t0 = 0;
+    own_p1 = n_pairs;
+    own_t1 = n_trips;
+    own_i0 = 0;
+    own_i1 = n;
+    if (world <= 1 || n <= 0) return MBPOL_OK;
+    std::vector<int64_t> W(n + 1), ps(n + 1), qs(n + 1);
+    CK(cudaMemcpyAsync(W.data(), weight.ptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ps.data(), pstart.ptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(qs.data(), qstart.ptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    auto bound = [&](int r) -> int {
+        if (r <= 0) return 0;
+        if (r >= world) return n;
+        const double target = (double)W[n] * r / world;
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if ((double)W[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    own_i0 = bound(rank);
+    own_i1 = bound(rank + 1);
+    own_p0 = ps[own_i0];
+    own_p1 = ps[own_i1];
+    int64_t t01[2] = {0, 0};
+    const int64_t q0 = qs[own_i0], q1 = qs[own_i1];
+    CK(cudaMemcpyAsync(&t01[0], tstart.as<int64_t>() + q0, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&t01[1], tstart.as<int64_t>() + q1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    own_t0 = t01[0];
+    own_t1 = t01[1];
+    return MBPOL_OK;
+}
+
+int ContributionIndex::build(const int32_t* tuples, int width, int64_t first, int64_t count, int n_mol,
+                             DeviceBuf& cub_tmp, cudaStream_t s, std::string& err) {
+    n_entries = count * width;
+    int rc;
+    if ((rc = off.reserve(sizeof(int64_t) * (n_mol + 1), err))) return rc;
+    if (n_entries == 0) {
+        CK(cudaMemsetAsync(off.ptr, 0, sizeof(int64_t) * (n_mol + 1), s));
+        return MBPOL_OK;
+    }
+    if (n_entries > 0x7FFFFFFFLL) {
+        err = "too many tuple contributions for 32-bit entry ids";
+        return MBPOL_EINVAL;
+    }
+    if ((rc = keys_in.reserve(sizeof(int32_t) * n_entries, err))) return rc;
+    if ((rc = vals_in.reserve(sizeof(int32_t) * n_entries, err))) return rc;
+    if ((rc = keys.reserve(sizeof(int32_t) * n_entries, err))) return rc;
+    if ((rc = vals.reserve(sizeof(int32_t) * n_entries, err))) return rc;
+    contribution_keys_kernel<<<blocks(n_entries), 128, 0, s>>>(first, count, width, tuples, keys_in.as<int32_t>(),
+                                                               vals_in.as<int32_t>());
+    int bits = 1;
+    while ((1LL << bits) < n_mol) ++bits;
+    size_t bytes = 0;
+    // LSD radix sort is stable: inside one molecule the entries stay in ascending (tuple, role) order -> the
+    // summation order of the force reduction is fixed by the canonical tuple order alone.
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in.as<int32_t>(), keys.as<int32_t>(),
+                                       vals_in.as<int32_t>(), vals.as<int32_t>(), (int)n_entries, 0, bits, s));
+    if ((rc = cub_tmp.reserve(bytes, err))) return rc;
+    CK(cub::DeviceRadixSort::SortPairs(cub_tmp.ptr, bytes, keys_in.as<int32_t>(), keys.as<int32_t>(),
+                                       vals_in.as<int32_t>(), vals.as<int32_t>(), (int)n_entries, 0, bits, s));
+    segment_offsets_kernel<<<blocks(n_mol + 1), 128, 0, s>>>(n_mol, n_entries, keys.as<int32_t>(), off.as<int64_t>());
+    CK(cudaGetLastError());
+    return MBPOL_OK;
+}
+
+}  // namespace mbpol
