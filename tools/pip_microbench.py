@@ -40,13 +40,23 @@ def fp64_instr(cubin):
     return len(re.findall(r"^(?:fma|mul|add)\.rn\.f64", txt, flags=re.M))
 
 
+def ptx_block(cubin, default):
+    ptx = os.path.join(os.path.dirname(cubin), os.path.basename(cubin)[:5] + "_eval.ptx")
+    if os.path.exists(ptx):
+        m = re.search(r"^\.maxntid (\d+)", open(ptx).read(), flags=re.M)
+        if m:
+            return int(m.group(1))
+    return default
+
+
 def run(cubin, waves, block, reps, ref):
     name = os.path.basename(cubin)[:5]
+    block = ptx_block(cubin, block)
     nv = N_VARS[name]
     data = np.fromfile(cubin, dtype=np.uint8)
     mod = ck(cu.cuModuleLoadData(data.ctypes.data))
     fn = ck(cu.cuModuleGetFunction(mod, f"{name}_eval".encode()))
-    n = 148 * block * waves
+    n = 148 * 256 * waves
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(nv, n, dtype=torch.float64, device="cuda", generator=g) * 1.2 + 0.1
     out = torch.zeros(nv + 1, n, dtype=torch.float64, device="cuda")
