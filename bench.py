@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the MB-pol 2B+3B many-body path (BASELINE.json metric: water-steps/s; % of the FP64 roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload synthetic_262144] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A step = one full force evaluation of the box: tuple-list build (every step, like the Reference platform), 2B and 3B
+PIP energy + gradient over every listed dimer / trimer, switching functions, deterministic force reduction [+ position
+broadcast and force/energy all-reduce for N > 1].  Workload: the synthetic liquid-water box of BASELINE.json
+(configs[4], 262,144 waters = 8^3 tiles of the reference's 512-water cell) at every N -> strong scaling.
+
+  value      water-steps/s with positions already resident in HBM (device pointers through the C ABI)
+  e2e        the same through the plugin-style API with HOST buffers: pinned host positions -> device, forces and
+             energies -> host, every step
+  roofline   the dominant kernel (pip3b_eval): algorithmic flops (111,818 per trimer) / its CUDA-event
+             time inside the timed steps, against the FP64 FMA-pipe peak measured on this GPU by a register-resident
+             DFMA loop (MEASURED_PEAKS.json carries no FP64 entry); nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TF
+  cpu_baseline / --impl reference : the reference's own CPU code (oracle/_ref, single thread = the Reference platform)
+             on a bounded random sample of the same workload's tuples, extrapolated by the tuple counts.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP2, FLOP3 = 30601, 111818
+NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def make_forces(n_mol, stride=3):
+    from mbpol_openmm_plugin_b200 import MBPolThreeBodyForce, MBPolTwoBodyForce
+    from mbpol_openmm_plugin_b200.systems import particle_indices
+    idx = particle_indices(n_mol, stride).tolist()
+    out = []
+    for cls, cut in ((MBPolTwoBodyForce, 0.65), (MBPolThreeBodyForce, 0.45)):       # python/mbpol.xml:31-36
+        f = cls()
+        f.setCutoff(cut)
+        f.setNonbondedMethod(cls.CutoffPeriodic)
+        f._particles = idx                      # bulk equivalent of n_mol addParticle() calls
+        out.append(f)
+    return out
+
+
+def cpu_reference_rate(pos_mol, box, n_dimers, n_trimers, seed=0):
+    """Reference code (oracle/_ref if built, else the C port) on a random sample of the workload's own tuples.
+    Returns (water-steps/s extrapolated by tuple counts, description)."""
+    from oracle.refbind import best
+    o = best()
+    posO = pos_mol[:, 0].copy()
+    t0 = time.perf_counter()
+    pairs = o.pairs(posO, box, True, 0.65)
+    trips = o.triplets(posO, box, True, 0.45)
+    t_lists = time.perf_counter() - t0
+    rng = np.random.default_rng(seed)
+    sp = pairs[rng.choice(len(pairs), min(n_dimers, len(pairs)), replace=False)]
+    st = trips[rng.choice(len(trips), min(n_trimers, len(trips)), replace=False)]
+    n = len(pos_mol)
+    idx = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    pos = pos_mol.reshape(-1, 3)
+    t0 = time.perf_counter()
+    o.eval_2b(pos, idx, sp, box, True)
+    t2 = (time.perf_counter() - t0) / len(sp)
+    t0 = time.perf_counter()
+    o.eval_3b(pos, idx, st, box, True)
+    t3 = (time.perf_counter() - t0) / len(st)
+    step_s = t_lists + len(pairs) * t2 + len(trips) * t3
+    desc = (f"{len(sp)} dimers ({t2 * 1e6:.1f} us each) + {len(st)} trimers ({t3 * 1e6:.1f} us each) drawn at random from the "
+            f"{len(pairs)} / {len(trips)} tuples of the workload, full list build {t_lists:.2f} s; extrapolated by tuple counts; "
+            f"single thread ({o.kind})")
+    return n / step_s, desc, o.kind
+
+
+def run_reference_arm(args, workload, pos_mol, box):
+    """--impl reference: the reference's CPU implementation, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    rates = []
+    desc = kind = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r, desc, kind = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers, seed=i)
+        if i >= args.warmup:
+            rates.append((r, time.perf_counter() - t0))
+    value = float(np.mean([r for r, _ in rates]))
+    n = len(pos_mol)
+    line = {
+        "impl": "reference", "metric": "2B+3B PIP force evals/s (water-steps/s)", "value": value, "unit": "water-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n / value * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "waters": n, "cutoff_2b_nm": 0.65, "cutoff_3b_nm": 0.45, "periodic": True},
+        "cpu_baseline": {"value": value, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": "water-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synthetic_262144")
+    ap.add_argument("--ref-dimers", type=int, default=20000)
+    ap.add_argument("--ref-trimers", type=int, default=60000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from mbpol_openmm_plugin_b200.systems import WORKLOADS, synthetic_box
+    pos_mol, box = synthetic_box(WORKLOADS[args.workload])
+    n = len(pos_mol)
+
+    if args.impl == "reference":
+        args.ref_dimers, args.ref_trimers = min(args.ref_dimers, 4000), min(args.ref_trimers, 12000)
+        run_reference_arm(args, args.workload, pos_mol, box)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mbpol_openmm_plugin_b200 import MBPolContext, measure_fp64_peak
+    from mbpol_openmm_plugin_b200.distributed import CudaSliceEngine, DistributedForce
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak_tf, _ = measure_fp64_peak()
+
+    ctx = MBPolContext(3 * n, make_forces(n), box_nm=box.tolist(), device=local, rank=rank, world=world)
+    ctx.engine.set_timing(True)
+    dforce = DistributedForce(CudaSliceEngine(ctx), 3 * n, dev)
+    pos_dev = torch.as_tensor(pos_mol.reshape(-1, 3)).to(dev)
+    pos_host = torch.as_tensor(pos_mol.reshape(-1, 3)).pin_memory()
+    f_host = torch.zeros(3 * n, 3, dtype=torch.float64).pin_memory()
+    e_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    acc = {"pip3": 0.0, "pip2": 0.0, "lists": 0.0, "b2": 0.0, "b3": 0.0, "launches": 0, "n": 0, "t3": 0, "p2": 0}
+
+    def step_device():
+        dforce.step(pos_dev if rank == 0 else None)
+        st = ctx.engine.stats()
+        acc["pip3"] += st["ms_pip_3b"]; acc["pip2"] += st["ms_pip_2b"]; acc["lists"] += st["ms_lists"]
+        acc["b2"] += st["ms_2b"]; acc["b3"] += st["ms_3b"]; acc["launches"] += st["n_launches"]; acc["n"] += 1
+        acc["t3"], acc["p2"] = st["n_triplets_owned"], st["n_pairs_owned"]
+
+    def step_e2e():
+        if world == 1:
+            # public API with host arrays: C-ABI mbpol_eval_host copies positions in and forces / energies out
+            ctx.setPositions(pos_host.numpy())
+            ctx.setForceOutput(f_host.numpy())
+            ctx.calcForcesAndEnergy()
+        else:
+            energy, force = dforce.step(pos_host if rank == 0 else None)      # pinned host -> device -> broadcast
+            if rank == 0:
+                f_host.copy_(force, non_blocking=True)
+                e_host.copy_(energy, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    for k in acc:
+        acc[k] = 0 if isinstance(acc[k], int) else 0.0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = ctx.engine.stats()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        n_pairs, n_trips = stats["n_pairs"], stats["n_triplets"]
+        value = n * args.steps / (ms * 1e-3)
+        e2e = n * args.steps / (ms_e2e * 1e-3)
+        k = max(acc["n"], 1)
+        ms_pip3 = acc["pip3"] / k
+        achieved = acc["t3"] * FLOP3 / (ms_pip3 * 1e-3) / 1e12 if ms_pip3 > 0 else 0.0
+        ms_pip2 = acc["pip2"] / k
+        ach2 = acc["p2"] * FLOP2 / (ms_pip2 * 1e-3) / 1e12 if ms_pip2 > 0 else 0.0
+        from mbpol_openmm_plugin_b200 import _lib
+        ni3 = _lib.load().mbpol_pip_instruction_count(3)
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        line = {
+            "metric": "2B+3B PIP force evals/s (water-steps/s)", "value": value, "unit": "water-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "waters": n, "dimers": int(n_pairs), "trimers": int(n_trips),
+                       "cutoff_2b_nm": 0.65, "cutoff_3b_nm": 0.45, "periodic": True, "lists": "rebuilt every step",
+                       "parallelism": f"owner-molecule partition x{world}",
+                       "l2": "per-step working set (variables, gradients, force blocks: several GB) exceeds the 126 MB L2"},
+            "alg_tflops": (n_pairs * FLOP2 + n_trips * FLOP3) * args.steps / (ms * 1e-3) / 1e12,
+            "frac_of_nominal_fp64_peak": (n_pairs * FLOP2 + n_trips * FLOP3) * args.steps / (ms * 1e-3) / 1e12
+                                         / (NOMINAL_FP64_TF * world),
+            "e2e": {"value": e2e, "unit": "water-steps/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(pos_host.numel() * 8 * (2 if world == 1 else 1)),
+                    "d2h_bytes_per_step": int(f_host.numel() * 8 + 16)},
+            "gpu_launches": int(acc["launches"]),
+            "stage_ms": {"lists": acc["lists"] / k, "2b": acc["b2"] / k, "3b": acc["b3"] / k, "pip2b_eval": ms_pip2,
+                         "pip3b_eval": ms_pip3},
+            "roofline": {"bound": "fp64", "kernel": "pip3b_eval", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "measured on this GPU: register-resident DFMA loop (mbpol_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "nominal_peak": NOMINAL_FP64_TF, "frac_of_nominal": achieved / NOMINAL_FP64_TF,
+                         "fp64_instr_per_trimer": ni3,
+                         "fp64_pipe_issue_util": acc["t3"] / 32 * ni3 / (ms_pip3 * 1e-3) / (148 * 2 * sm_hz) if ms_pip3 > 0 else None,
+                         "share_of_step": ms_pip3 / (ms / args.steps), "pip2b_eval_tflops": ach2,
+                         "algorithmic_flops_per_launch": acc["t3"] * FLOP3},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, desc, kind = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers)
+            line["cpu_baseline"] = {"value": v, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

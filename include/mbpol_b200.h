@@ -68,6 +68,8 @@ typedef struct mbpol_stats {
     int64_t n_pairs_owned;  /* dimers / trimers evaluated by THIS context (owner range)  */
     int64_t n_triplets_owned;
     float   ms_lists, ms_2b, ms_3b, ms_reduce;   /* device time of the stages (CUDA events), 0 if timing disabled */
+    float   ms_pip_2b, ms_pip_3b;                /* the polynomial kernels alone (the roofline kernels)             */
+    int64_t n_launches;     /* kernels launched by the last mbpol_eval (library-internal CUB passes counted once each) */
 } mbpol_stats;
 
 /* replaces CalcMBPol*ForceKernel::initialize (MBPolReferenceKernels.cpp:341-360, 430-449) */

@@ -35,7 +35,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_triplets", C.c_int64), ("n_pairs_owned", C.c_int64),
                 ("n_triplets_owned", C.c_int64), ("ms_lists", C.c_float), ("ms_2b", C.c_float), ("ms_3b", C.c_float),
-                ("ms_reduce", C.c_float)]
+                ("ms_reduce", C.c_float), ("ms_pip_2b", C.c_float), ("ms_pip_3b", C.c_float), ("n_launches", C.c_int64)]
 
 
 class MBPolError(RuntimeError):

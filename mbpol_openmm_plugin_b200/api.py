@@ -248,6 +248,7 @@ class MBPolContext:
         self._pos = None
         self.energies = {}
         self._forces = None
+        self._force_out = None
 
     # -- plumbing used by the kernels ---------------------------------------------------------------------
     def _register(self, kernel, force):
@@ -261,7 +262,11 @@ class MBPolContext:
         if self._pos is None:
             raise MBPolError(_lib.EINVAL, "positions have not been set")
         if isinstance(self._pos, np.ndarray):
-            f = np.zeros_like(self._pos)
+            if self._force_out is not None:
+                f = self._force_out
+                f[...] = 0.0
+            else:
+                f = np.zeros_like(self._pos)
             e2, e3 = self.engine.eval_host(self._pos, f, flags)
         else:
             import torch
@@ -289,6 +294,13 @@ class MBPolContext:
             raise MBPolError(_lib.EINVAL, "Called setPositions() with the wrong number of positions")
         self._pos = p
         self._forces = None
+
+    def setForceOutput(self, array):
+        """Host evaluations write their forces into this (e.g. pinned) n_particles x 3 float64 array instead of a new one."""
+        if array is not None and (array.shape != (self.n_particles, 3) or array.dtype != np.float64 or
+                                  not array.flags.c_contiguous):
+            raise MBPolError(_lib.EINVAL, "force output must be a C-contiguous float64 array of shape (n_particles, 3)")
+        self._force_out = array
 
     def calcForcesAndEnergy(self, groups=0xFFFFFFFF):
         """ContextImpl::calcForcesAndEnergy for the registered kernels, honouring force groups

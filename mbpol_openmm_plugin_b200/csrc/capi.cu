@@ -31,7 +31,7 @@ struct mbpol_ctx {
     ContributionIndex ci2, ci3;
     DeviceBuf x2, r2, o2, e2, f2, x3, r3, o3, e3, f3;
     DeviceBuf f_mol, e_partial, d_energy, pos_stage, force_stage;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[6] = {}, evp[4] = {};      // stage events; events around the two polynomial kernels
     bool f_mol_valid = false;
 };
 
@@ -81,12 +81,16 @@ int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool
     const int32_t* idx = ctx->idx.as<int32_t>();
     if (order == 2) {
         launch_dimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), s);
+        if (ctx->timing) cudaEventRecord(ctx->evp[0], s);
         if ((rc = pip_launch(2, X.as<double>(), O.as<double>(), n, ld, s, &err))) return rc;
+        if (ctx->timing) cudaEventRecord(ctx->evp[1], s);
         launch_dimer_forces(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), O.as<double>(),
                             E.as<double>(), F.as<double>(), s);
     } else {
         launch_trimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), s);
+        if (ctx->timing) cudaEventRecord(ctx->evp[2], s);
         if ((rc = pip_launch(3, X.as<double>(), O.as<double>(), n, ld, s, &err))) return rc;
+        if (ctx->timing) cudaEventRecord(ctx->evp[3], s);
         launch_trimer_forces(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), O.as<double>(),
                              E.as<double>(), F.as<double>(), s);
     }
@@ -196,6 +200,7 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
         return bail(MBPOL_ECUDA, "copying particle indices failed");
     cudaMemset(ctx->d_energy.ptr, 0, 2 * sizeof(double));
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& e : ctx->evp) cudaEventCreate(&e);
     *out = ctx;
     return MBPOL_OK;
 }
@@ -204,6 +209,8 @@ void mbpol_destroy(mbpol_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evp)
         if (e) cudaEventDestroy(e);
     delete ctx;
 }
@@ -250,6 +257,7 @@ int mbpol_eval(mbpol_ctx* ctx, const double* pos_nm, double* force, double* ener
     CKC(cudaMemsetAsync(ctx->d_energy.ptr, 0, 2 * sizeof(double), s));
     ctx->stats = mbpol_stats{};
     ctx->f_mol_valid = false;
+    g_launches = 0;
     bool started = false;
     int rc;
     const bool p2 = is_periodic(ctx->method2), p3 = is_periodic(ctx->method3);
@@ -275,7 +283,10 @@ int mbpol_eval(mbpol_ctx* ctx, const double* pos_nm, double* force, double* ener
         cudaEventElapsedTime(&ctx->stats.ms_2b, ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&ctx->stats.ms_3b, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ctx->stats.ms_reduce, ctx->ev[3], ctx->ev[4]);
+        if (want2 && ctx->stats.n_pairs_owned > 0) cudaEventElapsedTime(&ctx->stats.ms_pip_2b, ctx->evp[0], ctx->evp[1]);
+        if (want3 && ctx->stats.n_triplets_owned > 0) cudaEventElapsedTime(&ctx->stats.ms_pip_3b, ctx->evp[2], ctx->evp[3]);
     }
+    ctx->stats.n_launches = g_launches;
     CKC(cudaGetLastError());
     return MBPOL_OK;
 }

@@ -9,6 +9,10 @@
 
 namespace mbpol {
 
+// kernels launched since the counter was last reset (mbpol_stats::n_launches); every <<<>>> site bumps it
+extern thread_local int64_t g_launches;
+#define MBPOL_COUNT_LAUNCH(n) (::mbpol::g_launches += (n))
+
 // ---- physical constants of the path --------------------------------------------------------------------------------
 // Unit conversions: openmmapi/include/openmm/internal/MBPolConstants.h:37-38
 constexpr double NM_TO_A = 10.0;

@@ -310,6 +310,7 @@ static int exclusive_scan(const int* in, int64_t* out, int64_t n, DeviceBuf& tmp
     int rc = tmp.reserve(bytes, err);
     if (rc) return rc;
     CK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, it, out, n + 1, s));
+    MBPOL_COUNT_LAUNCH(1);
     return MBPOL_OK;
 }
 
@@ -323,7 +324,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     int rc;
 #define RES(buf, count, type) if ((rc = buf.reserve(sizeof(type) * (size_t)(count), err))) return rc
     RES(posO, 3 * n, double);
-    gather_oxygens_kernel<<<blocks(n), 128, 0, s>>>(pos, idx, n, posO.as<double>());
+    gather_oxygens_kernel<<<blocks(n), 128, 0, s>>>(pos, idx, n, posO.as<double>()); MBPOL_COUNT_LAUNCH(1);
 
     // ---- grid ---------------------------------------------------------------------------------------------------
     // rows are only needed out to the largest finite cutoff in use; "no cutoff" (1e10) degenerates to one cell
@@ -339,7 +340,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         }
     } else {
         RES(scratch, 6, double);
-        bbox_kernel<<<1, 256, 0, s>>>(posO.as<double>(), n, scratch.as<double>());
+        bbox_kernel<<<1, 256, 0, s>>>(posO.as<double>(), n, scratch.as<double>()); MBPOL_COUNT_LAUNCH(1);
         double bb[6];
         CK(cudaMemcpyAsync(bb, scratch.ptr, sizeof bb, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -372,15 +373,16 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     RES(cell_members, n, int);
     CK(cudaMemsetAsync(cell_count.ptr, 0, sizeof(int) * (ncell + 1), s));
     CK(cudaMemsetAsync(cell_cursor.ptr, 0, sizeof(int) * ncell, s));
-    cell_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_of.as<int>(), cell_count.as<int>());
+    cell_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_of.as<int>(), cell_count.as<int>()); MBPOL_COUNT_LAUNCH(1);
     {
         size_t bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cell_count.as<int>(), cell_start.as<int>(), (int)ncell + 1, s));
         if ((rc = cub_tmp.reserve(bytes, err))) return rc;
         CK(cub::DeviceScan::ExclusiveSum(cub_tmp.ptr, bytes, cell_count.as<int>(), cell_start.as<int>(), (int)ncell + 1, s));
+        MBPOL_COUNT_LAUNCH(1);
     }
     cell_fill_kernel<<<blocks(n), 128, 0, s>>>(n, cell_of.as<int>(), cell_start.as<int>(), cell_cursor.as<int>(),
-                                               cell_members.as<int>());
+                                               cell_members.as<int>()); MBPOL_COUNT_LAUNCH(1);
 
     // ---- neighbour rows -----------------------------------------------------------------------------------------
     const double c2sq = want2 ? cut2 * cut2 : -1.0, c3sq = want3 ? cut3 * cut3 : -1.0;
@@ -395,7 +397,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
     CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
     row_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
-                                               c2sq, c3sq, cnt2.as<int>(), cnt3.as<int>());
+                                               c2sq, c3sq, cnt2.as<int>(), cnt3.as<int>()); MBPOL_COUNT_LAUNCH(1);
     if ((rc = exclusive_scan(cnt2.as<int>(), ro2.as<int64_t>(), n, cub_tmp, s, err))) return rc;
     if ((rc = exclusive_scan(cnt3.as<int>(), ro3.as<int64_t>(), n, cub_tmp, s, err))) return rc;
     int64_t tot[2];
@@ -406,7 +408,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     RES(nbr3, tot[1] + 1, int);
     row_fill_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
                                               c2sq, c3sq, ro2.as<int64_t>(), ro3.as<int64_t>(), nbr2.as<int>(),
-                                              nbr3.as<int>(), low2.as<int>(), low3.as<int>());
+                                              nbr3.as<int>(), low2.as<int>(), low3.as<int>()); MBPOL_COUNT_LAUNCH(1);
 
     // ---- pair lists (2B pairs, 3B hub pairs) ----------------------------------------------------------------------
     RES(pstart, n + 1, int64_t);
@@ -421,9 +423,9 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     RES(pairs, 2 * n_pairs + 2, int32_t);
     RES(qpairs, 2 * n_qpairs + 2, int32_t);
     emit_pairs_kernel<<<blocks(n), 128, 0, s>>>(n, ro2.as<int64_t>(), nbr2.as<int>(), low2.as<int>(),
-                                                pstart.as<int64_t>(), pairs.as<int32_t>());
+                                                pstart.as<int64_t>(), pairs.as<int32_t>()); MBPOL_COUNT_LAUNCH(1);
     emit_pairs_kernel<<<blocks(n), 128, 0, s>>>(n, ro3.as<int64_t>(), nbr3.as<int>(), low3.as<int>(),
-                                                qstart.as<int64_t>(), qpairs.as<int32_t>());
+                                                qstart.as<int64_t>(), qpairs.as<int32_t>()); MBPOL_COUNT_LAUNCH(1);
 
     // ---- triplets -------------------------------------------------------------------------------------------------
     RES(tcnt, n_qpairs + 1, int);
@@ -431,7 +433,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     CK(cudaMemsetAsync(tcnt.ptr, 0, sizeof(int) * (n_qpairs + 1), s));
     if (n_qpairs > 0)
         triplet_count_kernel<<<blocks(n_qpairs), 128, 0, s>>>(n_qpairs, qpairs.as<int32_t>(), low3.as<int>(),
-                                                              tcnt.as<int>());
+                                                              tcnt.as<int>()); MBPOL_COUNT_LAUNCH(1);
     if ((rc = exclusive_scan(tcnt.as<int>(), tstart.as<int64_t>(), n_qpairs, cub_tmp, s, err))) return rc;
     CK(cudaMemcpyAsync(&tot[0], tstart.as<int64_t>() + n_qpairs, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -440,11 +442,11 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     if (n_qpairs > 0)
         emit_triplets_kernel<<<blocks(n_qpairs), 128, 0, s>>>(n_qpairs, qpairs.as<int32_t>(), ro3.as<int64_t>(),
                                                               nbr3.as<int>(), low3.as<int>(), tstart.as<int64_t>(),
-                                                              trips.as<int32_t>());
+                                                              trips.as<int32_t>()); MBPOL_COUNT_LAUNCH(1);
     // ---- cumulative owner weights for the multi-GPU partition -------------------------------------------------------
     RES(weight, n + 1, int64_t);
     owner_weight_kernel<<<blocks(n + 1), 128, 0, s>>>(n, pstart.as<int64_t>(), qstart.as<int64_t>(),
-                                                      tstart.as<int64_t>(), want2, want3, weight.as<int64_t>());
+                                                      tstart.as<int64_t>(), want2, want3, weight.as<int64_t>()); MBPOL_COUNT_LAUNCH(1);
     CK(cudaGetLastError());
 #undef RES
     return MBPOL_OK;
@@ -506,7 +508,7 @@ int ContributionIndex::build(const int32_t* tuples, int width, int64_t first, in
     if ((rc = keys.reserve(sizeof(int32_t) * n_entries, err))) return rc;
     if ((rc = vals.reserve(sizeof(int32_t) * n_entries, err))) return rc;
     contribution_keys_kernel<<<blocks(n_entries), 128, 0, s>>>(first, count, width, tuples, keys_in.as<int32_t>(),
-                                                               vals_in.as<int32_t>());
+                                                               vals_in.as<int32_t>()); MBPOL_COUNT_LAUNCH(1);
     int bits = 1;
     while ((1LL << bits) < n_mol) ++bits;
     size_t bytes = 0;
@@ -517,7 +519,8 @@ int ContributionIndex::build(const int32_t* tuples, int width, int64_t first, in
     if ((rc = cub_tmp.reserve(bytes, err))) return rc;
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp.ptr, bytes, keys_in.as<int32_t>(), keys.as<int32_t>(),
                                        vals_in.as<int32_t>(), vals.as<int32_t>(), (int)n_entries, 0, bits, s));
-    segment_offsets_kernel<<<blocks(n_mol + 1), 128, 0, s>>>(n_mol, n_entries, keys.as<int32_t>(), off.as<int64_t>());
+    MBPOL_COUNT_LAUNCH(1);
+    segment_offsets_kernel<<<blocks(n_mol + 1), 128, 0, s>>>(n_mol, n_entries, keys.as<int32_t>(), off.as<int64_t>()); MBPOL_COUNT_LAUNCH(1);
     CK(cudaGetLastError());
     return MBPOL_OK;
 }

@@ -13,9 +13,11 @@
 
 namespace mbpol {
 
+thread_local int64_t g_launches = 0;
+
 namespace {
 
-#include "gen/pip_cubins.inc"   // pip2b_cubin[], pip3b_cubin[], PIP2B_NINSTR, PIP3B_NINSTR, PIP_BLOCK
+#include "gen/pip_cubins.inc"   // pip{2b,3b}_cubin[], PIP{2B,3B}_NINSTR / _SMEM (dynamic shared bytes) / _BLOCK
 
 struct DriverApi {
     CUresult (*moduleLoadData)(CUmodule*, const void*) = nullptr;
@@ -23,6 +25,7 @@ struct DriverApi {
     CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                              void**, void**) = nullptr;
     CUresult (*getErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     bool ok = false;
 };
 
@@ -54,7 +57,8 @@ int ensure_loaded(int dev, std::string* err) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_api.ok) {
         if (!entry("cuModuleLoadData", g_api.moduleLoadData) || !entry("cuModuleGetFunction", g_api.moduleGetFunction) ||
-            !entry("cuLaunchKernel", g_api.launchKernel) || !entry("cuGetErrorString", g_api.getErrorString)) {
+            !entry("cuLaunchKernel", g_api.launchKernel) || !entry("cuGetErrorString", g_api.getErrorString) ||
+            !entry("cuFuncSetAttribute", g_api.funcSetAttribute)) {
             if (err) *err = "CUDA driver entry points unavailable (no GPU driver?)";
             return MBPOL_ECUDA;
         }
@@ -67,7 +71,9 @@ int ensure_loaded(int dev, std::string* err) {
     if ((r = g_api.moduleLoadData(&m.mod2, pip2b_cubin)) != CUDA_SUCCESS ||
         (r = g_api.moduleLoadData(&m.mod3, pip3b_cubin)) != CUDA_SUCCESS ||
         (r = g_api.moduleGetFunction(&m.fn2, m.mod2, "pip2b_eval")) != CUDA_SUCCESS ||
-        (r = g_api.moduleGetFunction(&m.fn3, m.mod3, "pip3b_eval")) != CUDA_SUCCESS) {
+        (r = g_api.moduleGetFunction(&m.fn3, m.mod3, "pip3b_eval")) != CUDA_SUCCESS ||
+        (r = g_api.funcSetAttribute(m.fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP2B_SMEM)) != CUDA_SUCCESS ||
+        (r = g_api.funcSetAttribute(m.fn3, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP3B_SMEM)) != CUDA_SUCCESS) {
         if (err) *err = "loading the sm_100a PIP cubins failed: " + cu_msg(r);
         m = DeviceModule();
         return MBPOL_ECUDA;
@@ -98,13 +104,15 @@ int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, c
     if (rc != MBPOL_OK) return rc;
     unsigned un = (unsigned)n, uld = (unsigned)ld;
     void* args[] = {(void*)&x, (void*)&out, (void*)&un, (void*)&uld};
-    const unsigned grid = (unsigned)((n + PIP_BLOCK - 1) / PIP_BLOCK);
-    CUresult r = g_api.launchKernel(order == 2 ? g_dev[dev].fn2 : g_dev[dev].fn3, grid, 1, 1, PIP_BLOCK, 1, 1, 0,
+    const unsigned block = order == 2 ? PIP2B_BLOCK : PIP3B_BLOCK, smem = order == 2 ? PIP2B_SMEM : PIP3B_SMEM;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    CUresult r = g_api.launchKernel(order == 2 ? g_dev[dev].fn2 : g_dev[dev].fn3, grid, 1, 1, block, 1, 1, smem,
                                     (CUstream)s, args, nullptr);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "launch of the PIP kernel failed: " + cu_msg(r);
         return MBPOL_ECUDA;
     }
+    MBPOL_COUNT_LAUNCH(1);
     return MBPOL_OK;
 }
 

@@ -81,26 +81,26 @@ void launch_force_reduce(const ContributionIndex& ci, int width, const double* f
                          bool accumulate, cudaStream_t s) {
     if (n_mol <= 0) return;
     force_reduce_kernel<<<blocks(9LL * n_mol, 288), 288, 0, s>>>(ci.off.as<int64_t>(), ci.vals.as<int32_t>(), width,
-                                                                  f_tuple, n_mol, f_mol, accumulate ? 1 : 0);
+                                                                  f_tuple, n_mol, f_mol, accumulate ? 1 : 0); MBPOL_COUNT_LAUNCH(1);
 }
 
 void launch_force_scatter(const double* f_mol, const int32_t* idx, int n_mol, double* force, cudaStream_t s) {
     if (n_mol <= 0) return;
-    force_scatter_kernel<<<blocks(9LL * n_mol, 288), 288, 0, s>>>(f_mol, idx, n_mol, force);
+    force_scatter_kernel<<<blocks(9LL * n_mol, 288), 288, 0, s>>>(f_mol, idx, n_mol, force); MBPOL_COUNT_LAUNCH(1);
 }
 
 void launch_force_scatter_fixed(const double* f_mol, const int32_t* idx, int n_mol, long long* buf, int padded,
                                 cudaStream_t s) {
     if (n_mol <= 0) return;
-    force_scatter_fixed_kernel<<<blocks(9LL * n_mol, 288), 288, 0, s>>>(f_mol, idx, n_mol, buf, padded);
+    force_scatter_fixed_kernel<<<blocks(9LL * n_mol, 288), 288, 0, s>>>(f_mol, idx, n_mol, buf, padded); MBPOL_COUNT_LAUNCH(1);
 }
 
 void launch_energy_sum(const double* e, int64_t n, double* partial, double* out, cudaStream_t s) {
     int nb = (int)((n + ESUM_BLOCK - 1) / ESUM_BLOCK);
     if (nb > ESUM_MAX_BLOCKS) nb = ESUM_MAX_BLOCKS;
     if (nb < 1) nb = 1;
-    energy_partial_kernel<<<nb, ESUM_BLOCK, 0, s>>>(e, n, partial);
-    energy_final_kernel<<<1, ESUM_MAX_BLOCKS, 0, s>>>(partial, nb, out);
+    energy_partial_kernel<<<nb, ESUM_BLOCK, 0, s>>>(e, n, partial); MBPOL_COUNT_LAUNCH(1);
+    energy_final_kernel<<<1, ESUM_MAX_BLOCKS, 0, s>>>(partial, nb, out); MBPOL_COUNT_LAUNCH(1);
 }
 
 }  // namespace mbpol

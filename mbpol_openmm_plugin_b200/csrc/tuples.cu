@@ -352,23 +352,23 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 void launch_dimer_vars(const double* pos, const int32_t* idx, const int32_t* pairs, int64_t first, int64_t n, int64_t ld,
                        BoxArg box, double* x, double* rinv, cudaStream_t s) {
-    if (n > 0) dimer_vars_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, pairs, first, n, ld, box, x, rinv);
+    if (n > 0) dimer_vars_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, pairs, first, n, ld, box, x, rinv); MBPOL_COUNT_LAUNCH(1);
 }
 void launch_trimer_vars(const double* pos, const int32_t* idx, const int32_t* trips, int64_t first, int64_t n, int64_t ld,
                         BoxArg box, double* x, double* rinv, cudaStream_t s) {
-    if (n > 0) trimer_vars_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, trips, first, n, ld, box, x, rinv);
+    if (n > 0) trimer_vars_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, trips, first, n, ld, box, x, rinv); MBPOL_COUNT_LAUNCH(1);
 }
 void launch_dimer_forces(const double* pos, const int32_t* idx, const int32_t* pairs, int64_t first, int64_t n, int64_t ld,
                          BoxArg box, const double* x, const double* rinv, const double* poly, double* e, double* f,
                          cudaStream_t s) {
     if (n > 0)
-        dimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, pairs, first, n, ld, box, x, rinv, poly, e, f);
+        dimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, pairs, first, n, ld, box, x, rinv, poly, e, f); MBPOL_COUNT_LAUNCH(1);
 }
 void launch_trimer_forces(const double* pos, const int32_t* idx, const int32_t* trips, int64_t first, int64_t n,
                           int64_t ld, BoxArg box, const double* x, const double* rinv, const double* poly, double* e,
                           double* f, cudaStream_t s) {
     if (n > 0)
-        trimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, trips, first, n, ld, box, x, rinv, poly, e, f);
+        trimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, trips, first, n, ld, box, x, rinv, poly, e, f); MBPOL_COUNT_LAUNCH(1);
 }
 
 }  // namespace mbpol

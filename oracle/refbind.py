@@ -140,3 +140,84 @@ class Ref:
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+class Port:
+    """Our plain-C restatement (oracle/mbpol_oracle.c -> oracle/liboracle.so).  kind = "port"."""
+
+    kind = "port"
+
+    def __init__(self, path=PORT_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built; run `make -C oracle port`")
+        L = self.lib = C.CDLL(path)
+        data = os.path.join(HERE, "..", "mbpol_openmm_plugin_b200", "data")
+        self._keep = []
+        u16p, u8p = C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)
+        L.port_set_tables.argtypes = [C.c_int, C.c_int, C.c_int, _dp, u16p, u8p]
+        L.port_set_tables.restype = None
+        for order, name in ((2, "pip2b"), (3, "pip3b")):
+            t = np.load(os.path.join(data, name + ".npz"))
+            coef = np.ascontiguousarray(t["coef"], dtype=np.float64)
+            mc = np.ascontiguousarray(t["mono_coef"], dtype=np.uint16)
+            mv = np.ascontiguousarray(t["mono_vars"], dtype=np.uint8)
+            self._keep += [coef, mc, mv]
+            L.port_set_tables(order, int(t["n_vars"]), len(mc), _d(coef), mc.ctypes.data_as(u16p), mv.ctypes.data_as(u8p))
+        L.port_poly.restype = C.c_double
+        L.port_poly.argtypes = [C.c_int, _dp, _dp]
+        for fn in (L.port_pairs, L.port_triplets):
+            fn.restype = C.c_long
+            fn.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_double, _ip, C.c_long]
+        for fn in (L.port_eval_2b, L.port_eval_3b):
+            fn.restype = C.c_double
+            fn.argtypes = [_dp, _dp, _ip, _ip, C.c_long, _dp, C.c_int, _dp, _dp]
+
+    def poly(self, order, x):
+        x = _f64(x)
+        g = np.zeros(len(x))
+        return self.lib.port_poly(order, _d(x), _d(g)), g
+
+    def _list(self, fn, width, posO, box, pbc, cutoff):
+        posO = _f64(posO)
+        box = _f64(box if box is not None else [0, 0, 0])
+        n = len(posO)
+        cap = max(1024, 64 * n)
+        while True:
+            out = np.empty((cap, width), dtype=np.int32)
+            m = fn(_d(posO), n, _d(box), int(bool(pbc)), float(cutoff), out.ctypes.data_as(_ip), cap)
+            if m <= cap:
+                return out[:m]
+            cap = m
+
+    def pairs(self, posO, box, pbc, cutoff):
+        return self._list(self.lib.port_pairs, 2, posO, box, pbc, cutoff)
+
+    def triplets(self, posO, box, pbc, cutoff):
+        return self._list(self.lib.port_triplets, 3, posO, box, pbc, cutoff)
+
+    def _eval(self, fn, width, pos, idx, tuples, box, pbc, each):
+        pos = _f64(pos)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        tup = np.ascontiguousarray(tuples, dtype=np.int32)
+        box = _f64(box if box is not None else [0, 0, 0])
+        f = np.zeros_like(pos)
+        e_each = np.zeros(len(tup)) if each else None
+        f_each = np.zeros((len(tup), 3 * width, 3)) if each else None
+        e = fn(_d(pos), _d(f), idx.ctypes.data_as(_ip), tup.ctypes.data_as(_ip), len(tup), _d(box), int(bool(pbc)),
+               _d(e_each) if each else None, _d(f_each) if each else None)
+        return (e, f, e_each, f_each) if each else (e, f)
+
+    def eval_2b(self, pos, idx, pairs, box, pbc, cutoff=None, each=False):
+        return self._eval(self.lib.port_eval_2b, 2, pos, idx, pairs, box, pbc, each)
+
+    def eval_3b(self, pos, idx, trip, box, pbc, cutoff=None, each=False):
+        return self._eval(self.lib.port_eval_3b, 3, pos, idx, trip, box, pbc, each)
+
+
+def have_port():
+    return os.path.exists(PORT_SO)
+
+
+def best():
+    """The strongest checker available: the reference's own code if it was built, else the port."""
+    return Ref() if have_ref() else Port()

@@ -1,0 +1,62 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/mbpol_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, has_cuda
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mbpol_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbpol_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from mbpol_openmm_plugin_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mbpol_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_no_libcuda_link_dependency():
+    import subprocess
+    from mbpol_openmm_plugin_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out          # driver entry points are resolved at run time (pip_module.cu)
+
+
+def test_work_model_constants():
+    from mbpol_openmm_plugin_b200 import _lib
+    L = _lib.load()
+    assert _lib.FLOP_PER_DIMER == 30601 and _lib.FLOP_PER_TRIMER == 111818
+    assert 25000 < L.mbpol_pip_instruction_count(2) < 40000
+    assert 60000 < L.mbpol_pip_instruction_count(3) < 100000
+    assert L.mbpol_pip_instruction_count(4) == -1
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    """No CPU fallback: creating a context without a CUDA device is an error, not a silent downgrade."""
+    from mbpol_openmm_plugin_b200 import MBPolContext, MBPolError, MBPolTwoBodyForce
+    f = MBPolTwoBodyForce()
+    f.addParticle([0, 1, 2])
+    f.addParticle([3, 4, 5])
+    with pytest.raises(MBPolError) as e:
+        MBPolContext(6, [f])
+    assert e.value.code == -2 and "no CUDA device" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (checked on the sources)."""
+    pkg = os.path.join(ROOT, "mbpol_openmm_plugin_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "refbind" not in src and "liboracle" not in src and "libmbpol_ref" not in src, fn

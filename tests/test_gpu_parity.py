@@ -1,0 +1,306 @@
+"""Parity of the CUDA path (through the C ABI) against the oracles, on a real GPU.
+
+Bars (BASELINE.json north_star): tuple lists bit-exact; energies within 1e-9 relative; forces within 1e-6 kJ/mol/nm
+max-abs.  The checker is the reference's own code (oracle/_ref) when its build travelled with the repo, else the C port.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, make_context
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-9          # relative energy tolerance
+F_ATOL = 1e-6          # kJ/mol/nm
+
+
+def check_case(ctx, g, e_keys=("e2", "e3")):
+    e2, e3 = ctx.energies["CalcMBPolTwoBodyForce"], ctx.energies["CalcMBPolThreeBodyForce"]
+    assert abs(e2 - g["e2"]) <= E_RTOL * max(abs(float(g["e2"])), 1e-9)
+    assert abs(e3 - g["e3"]) <= E_RTOL * max(abs(float(g["e3"])), 1e-9)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_fixture_host_arrays(case):
+    """C-ABI call with HOST buffers (mbpol_eval_host): lists, energies, forces vs the committed reference outputs."""
+    g = load_golden(case)
+    n = len(g["pos_mol"])
+    ctx = make_context(n, g["box"], bool(g["pbc"]), float(g["cut2"]), float(g["cut3"]))
+    ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+    ctx.getPotentialEnergy()
+    assert np.array_equal(ctx.getPairs(), g["pairs"].reshape(-1, 2))            # bit-exact, canonical order
+    assert np.array_equal(ctx.getTriplets(), g["triplets"].reshape(-1, 3))
+    check_case(ctx, g)
+    f = ctx.getForces()
+    assert isinstance(f, np.ndarray)
+    assert np.abs(f - (g["f2"] + g["f3"])).max() < F_ATOL
+
+
+@pytest.mark.parametrize("case", ["water14_xml", "water256_bulk", "test_trimer_pbc_shifted"])
+def test_golden_fixture_device_tensors_and_m_sites(case):
+    """Device-resident positions, 4 particles per molecule (O,H1,H2,M) offset by +25 nm like
+    platforms/cuda/tests/TestCudaMBPolThreeBodyForce.cpp:66-150: M sites get exactly zero force."""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import with_virtual_sites
+    g = load_golden(case)
+    n = len(g["pos_mol"])
+    pos4 = with_virtual_sites(g["pos_mol"])
+    if bool(g["pbc"]):
+        pos4 = pos4 + np.array([float(g["box"][0]), 0.0, -2 * float(g["box"][2])])          # image of the whole system
+    ctx = make_context(n, g["box"], bool(g["pbc"]), float(g["cut2"]), float(g["cut3"]), stride=4)
+    ctx.setPositions(torch.as_tensor(pos4).cuda())
+    ctx.getPotentialEnergy()
+    f = ctx.getForces().cpu().numpy().reshape(n, 4, 3)
+    assert np.all(f[:, 3] == 0.0)
+    check_case(ctx, g)
+    assert np.abs(f[:, :3].reshape(-1, 3) - (g["f2"] + g["f3"])).max() < (2e-6 if bool(g["pbc"]) else F_ATOL)
+
+
+def test_reference_test_vectors_on_gpu():
+    """The numbers printed in the reference's own C++ tests (kcal/mol, kcal/mol/A), tolerance tightened to 5e-8."""
+    from test_oracle import DIMER_E, DIMER_GRAD, TRIMER_E, TRIMER_GRAD
+    for case, which, E, G in (("test_dimer", 2, DIMER_E, DIMER_GRAD), ("test_trimer", 3, TRIMER_E, TRIMER_GRAD)):
+        g = load_golden(case)
+        ctx = make_context(len(g["pos_mol"]), None, False, 10.0, 10.0, which=(which,))
+        ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+        e = ctx.getPotentialEnergy()
+        assert abs(e / 4.184 - E) < 5e-9
+        np.testing.assert_allclose(-ctx.getForces() / 41.84, G, atol=6e-8)
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_bare_polynomial(order):
+    import os
+    import torch
+    from conftest import GOLDEN
+    from mbpol_openmm_plugin_b200 import pip_eval
+    g = np.load(os.path.join(GOLDEN, "poly_values.npz"))
+    k = str(order)
+    x = torch.as_tensor(np.ascontiguousarray(g["x" + k].T)).cuda()
+    e, grad = pip_eval(order, x)
+    e, grad = e.cpu().numpy(), grad.cpu().numpy().T
+    assert np.abs(e - g["e" + k]).max() <= 1e-12 * np.abs(g["e" + k]).max()
+    assert np.abs(grad - g["g" + k]).max() <= 1e-12 * np.abs(g["g" + k]).max()
+
+
+@pytest.mark.parametrize("case", ["water14_nocut", "water256_bulk"])
+def test_per_tuple_parity(case, checker):
+    """energy and 6x3 / 9x3 force block of every single tuple against the oracle (before any summation)"""
+    from mbpol_openmm_plugin_b200 import eval_tuples
+    g = load_golden(case)
+    pbc = bool(g["pbc"])
+    box = g["box"] if pbc else None
+    n = len(g["pos_mol"])
+    pos = g["pos_mol"].reshape(-1, 3)
+    idx = np.arange(3 * n).reshape(n, 3)
+    for order, tuples in ((2, g["pairs"].reshape(-1, 2)), (3, g["triplets"].reshape(-1, 3))):
+        e, f = eval_tuples(order, g["pos_mol"], tuples, box)
+        if checker.kind == "reference":
+            er, fr = (checker.each_2b if order == 2 else checker.each_3b)(g["pos_mol"], tuples, box, pbc)
+        else:
+            _, _, er, fr = (checker.eval_2b if order == 2 else checker.eval_3b)(pos, idx, tuples, box, pbc, each=True)
+        assert np.abs(e - er).max() <= 1e-9 * max(np.abs(er).max(), 1e-9)
+        assert np.abs(f - fr).max() < F_ATOL
+
+
+def test_lists_edge_cases():
+    """coincident points, tiny systems, empty lists (TestReferenceThreeNeighborList.cpp:60-78 on the GPU list build)"""
+    base = np.array([[0.0, 0, 0], [0.09, 0.03, 0], [-0.03, 0.09, 0]])
+    O = np.array([[1.4, 0, 0], [1.0, 0, 0], [1.0, 0, 0], [1.0, 0, 0]])
+    pos = O[:, None, :] + base[None]
+    ctx = make_context(4, None, False, 1.2, 1.2)
+    ctx.setPositions(pos.reshape(-1, 3))
+    ctx.getPotentialEnergy()                      # coincident oxygens: r < 2 A early-out -> zero, but they are LISTED
+    assert len(ctx.getTriplets()) == 4 and len(ctx.getPairs()) == 6
+    ctx = make_context(4, None, False, 0.1, 0.1)
+    ctx.setPositions(pos.reshape(-1, 3))
+    assert ctx.getPotentialEnergy() == 0.0
+    assert ctx.getTriplets().tolist() == [[3, 2, 1]] and len(ctx.getPairs()) == 3
+    assert not np.any(ctx.getForces())
+    for n in (1, 2):                              # one molecule: nothing; two: a pair, no triplet
+        ctx = make_context(n, None, False, 1.0, 1.0)
+        ctx.setPositions((pos[:n] + np.arange(n)[:, None, None] * 0.3).reshape(-1, 3))
+        ctx.getPotentialEnergy()
+        assert len(ctx.getPairs()) == n - 1 and len(ctx.getTriplets()) == 0
+
+
+def test_run_to_run_determinism_is_bitwise():
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    ctx = make_context(len(pos), box, True)
+    p = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    out = []
+    for _ in range(3):
+        ctx.setPositions(p)
+        e = ctx.getPotentialEnergy()
+        out.append((e, ctx.getForces().clone()))
+    assert out[0][0] == out[1][0] == out[2][0]
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][1], out[2][1])
+
+
+def test_synthetic_4096_against_oracle(checker):
+    """BASELINE config 3: full lists bit-exact, energies to 1e-9, a force sample to 1e-6; plus invariants."""
+    import torch
+    from oracle.refbind import canonical
+    from mbpol_openmm_plugin_b200.systems import particle_indices, synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    ctx = make_context(n, box, True)
+    p = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    ctx.setPositions(p)
+    e = ctx.getPotentialEnergy()
+    f = ctx.getForces().cpu().numpy()
+    pairs, trips = ctx.getPairs(), ctx.getTriplets()
+    posO = pos[:, 0].copy()
+    if checker.kind == "reference":               # the port's list build is O(n^2): use it only if it must be
+        assert np.array_equal(pairs, canonical(checker.pairs(posO, box, True, 0.65)))
+        assert np.array_equal(trips, canonical(checker.triplets(posO, box, True, 0.45)))
+    assert 17.5 * n < len(pairs) < 19.5 * n and 23 * n < len(trips) < 28 * n        # SURVEY.md 8d densities
+    # sorted, strictly ordered, unique
+    assert np.all(pairs[:, 0] > pairs[:, 1]) and np.all(trips[:, 0] > trips[:, 1]) and np.all(trips[:, 1] > trips[:, 2])
+    key = trips[:, 0].astype(np.int64) * n * n + trips[:, 1].astype(np.int64) * n + trips[:, 2]
+    assert np.all(np.diff(key) > 0)
+    # per-tuple energies of a random sample against the oracle, and the full sums if the reference build is here
+    from mbpol_openmm_plugin_b200 import eval_tuples
+    rng = np.random.default_rng(0)
+    idx = particle_indices(n)
+    for order, tuples in ((2, pairs), (3, trips)):
+        sel = np.sort(rng.choice(len(tuples), 1500, replace=False))
+        eg, fg = eval_tuples(order, pos, tuples[sel], box)
+        if checker.kind == "reference":
+            er, fr = (checker.each_2b if order == 2 else checker.each_3b)(pos, tuples[sel], box, True)
+        else:
+            _, _, er, fr = (checker.eval_2b if order == 2 else checker.eval_3b)(pos.reshape(-1, 3), idx, tuples[sel], box,
+                                                                                 True, each=True)
+        assert np.abs(eg - er).max() <= 1e-9 * np.abs(er).max() and np.abs(fg - fr).max() < F_ATOL
+    if checker.kind == "reference":
+        e2, f2 = checker.eval_2b(pos.reshape(-1, 3), idx, pairs, box, True, 0.65)
+        e3, f3 = checker.eval_3b(pos.reshape(-1, 3), idx, trips, box, True, 0.45)
+        assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= E_RTOL * abs(e2)
+        assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= E_RTOL * abs(e3)
+        assert np.abs(f - (f2 + f3)).max() < F_ATOL
+    # size-independent properties: Newton's third law and invariance under whole-box translations of molecules
+    assert np.abs(f.sum(axis=0)).max() < 1e-6
+    shifted = pos.copy()
+    shifted[::7] += np.array([box[0], 0, 0])
+    shifted[::5] -= np.array([0, 2 * box[1], box[2]])
+    ctx.setPositions(torch.as_tensor(shifted.reshape(-1, 3)).cuda())
+    e_s = ctx.getPotentialEnergy()
+    assert abs(e_s - e) <= 1e-9 * abs(e)
+    assert np.abs(ctx.getForces().cpu().numpy() - f).max() < 2e-6
+
+
+def test_owner_partition_sums_to_full():
+    """multi-GPU partition on one device: the slices are disjoint, cover everything and add up to the full result"""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    p = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    full = make_context(n, box, True)
+    full.setPositions(p)
+    e_full = full.getPotentialEnergy()
+    f_full = full.getForces()
+    st_full = full.engine.stats()
+    world = 3
+    e_sum, f_sum, np_sum, nt_sum, flops = 0.0, torch.zeros_like(f_full), 0, 0, []
+    for r in range(world):
+        ctx = make_context(n, box, True, rank=r, world=world)
+        ctx.setPositions(p)
+        e_sum += ctx.getPotentialEnergy()
+        f_sum += ctx.getForces()
+        st = ctx.engine.stats()
+        assert (st["n_pairs"], st["n_triplets"]) == (st_full["n_pairs"], st_full["n_triplets"])
+        np_sum += st["n_pairs_owned"]
+        nt_sum += st["n_triplets_owned"]
+        flops.append(st["n_pairs_owned"] * 30601 + st["n_triplets_owned"] * 111818)
+    assert (np_sum, nt_sum) == (st_full["n_pairs"], st_full["n_triplets"])
+    assert abs(e_sum - e_full) <= 1e-11 * abs(e_full)
+    assert (f_sum - f_full).abs().max().item() < 1e-8
+    assert max(flops) / (sum(flops) / world) < 1.02                  # balanced by the 2B+3B work model
+
+
+def test_error_behaviour():
+    from mbpol_openmm_plugin_b200 import MBPolError, _lib
+    g = load_golden("water256_bulk")
+    n = len(g["pos_mol"])
+    ctx = make_context(n, g["box"], True)
+    with pytest.raises(MBPolError):
+        ctx.setPositions(np.zeros((5, 3)))                           # wrong number of positions
+    ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+    ctx.setPeriodicBoxVectors([1.2, 1.2, 1.2])                       # box shrank below 2 x cutoff
+    with pytest.raises(MBPolError) as e:                             # MBPolReferenceKernels.cpp:384-391
+        ctx.getPotentialEnergy()
+    assert e.value.code == _lib.EBOX and "less than twice the cutoff" in e.value.message
+    ctx.setPeriodicBoxVectors(g["box"].tolist())
+    ctx.getPotentialEnergy()
+    check_case(ctx, g)                                               # the context recovers
+    with pytest.raises(MBPolError) as e:                             # MBPolReferenceKernels.cpp:402-403
+        ctx.engine.update_particles(np.arange(6, dtype=np.int32).reshape(2, 3))
+    assert e.value.code == _lib.ECHANGED
+    with pytest.raises(MBPolError):
+        ctx.engine.eval_host(g["pos_mol"].reshape(-1, 3), None, 0)   # neither 2B nor 3B requested
+
+
+def test_force_groups_and_parameter_update():
+    g = load_golden("water14_xml")
+    n = len(g["pos_mol"])
+    ctx = make_context(n, None, False, 0.65, 0.45)
+    ctx.forces[1].setForceGroup(3)
+    ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+    e2 = ctx.getPotentialEnergy(groups=1 << 0)
+    f2 = ctx.getForces().copy()
+    e3 = ctx.getPotentialEnergy(groups=1 << 3)
+    f3 = ctx.getForces().copy()
+    assert abs(e2 - g["e2"]) <= E_RTOL * abs(g["e2"]) and abs(e3 - g["e3"]) <= E_RTOL * abs(g["e3"])
+    assert np.abs(f2 - g["f2"]).max() < F_ATOL and np.abs(f3 - g["f3"]).max() < F_ATOL
+    assert ctx.getPotentialEnergy(groups=1 << 5) == 0.0
+    # updateParametersInContext: swap the hydrogens of every molecule -> the PIPs are permutationally invariant
+    for f in ctx.forces:
+        for m in range(n):
+            o, h1, h2 = f.getParticleParameters(m)
+            f.setParticleParameters(m, [o, h2, h1])
+        f.updateParametersInContext(ctx)
+    e = ctx.getPotentialEnergy()
+    assert abs(e - (g["e2"] + g["e3"])) <= 1e-9 * abs(g["e2"] + g["e3"])
+
+
+def test_openmm_fixed_point_force_buffer():
+    """mbpol_add_forces_fixed_point: OpenMM CUDA convention, int64 = f * 2^32, SoA with padding
+    (platforms/cuda/src/kernels/twobodyForce.cu:442-457)"""
+    import torch
+    from mbpol_openmm_plugin_b200 import _lib
+    g = load_golden("water14_xml")
+    n = len(g["pos_mol"])
+    ctx = make_context(n, None, False, 0.65, 0.45)
+    ctx.setPositions(torch.as_tensor(g["pos_mol"].reshape(-1, 3)).cuda())
+    ctx.getPotentialEnergy()
+    padded = 64
+    buf = torch.zeros(3 * padded, dtype=torch.int64, device="cuda")
+    L = _lib.load()
+    _lib.check(L.mbpol_add_forces_fixed_point(ctx.engine.h, buf.data_ptr(), padded, None), ctx.engine.h)
+    torch.cuda.synchronize()
+    f = (buf.cpu().numpy().reshape(3, padded)[:, :3 * n].T / 2.0 ** 32)
+    assert np.abs(f - (g["f2"] + g["f3"])).max() < 1e-6
+
+
+def test_nocutoff_method_is_infinite_nonperiodic_cutoff():
+    from mbpol_openmm_plugin_b200 import MBPolContext, MBPolThreeBodyForce, MBPolTwoBodyForce
+    g = load_golden("water14_nocut")
+    n = len(g["pos_mol"])
+    fs = []
+    for cls in (MBPolTwoBodyForce, MBPolThreeBodyForce):
+        f = cls()
+        f.setNonbondedMethod(cls.NoCutoff)
+        f.setCutoff(0.3)                         # ignored for NoCutoff
+        for m in range(n):
+            f.addParticle([3 * m, 3 * m + 1, 3 * m + 2])
+        fs.append(f)
+    ctx = MBPolContext(3 * n, fs)
+    ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+    ctx.getPotentialEnergy()
+    check_case(ctx, g)
+    assert len(ctx.getTriplets()) == 364

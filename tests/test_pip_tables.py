@@ -1,0 +1,68 @@
+"""The committed polynomial data and the generated evaluator program, checked on the CPU.
+
+    reference SLP  --tools/extract_pip.py-->  monomial tables (data/pip{2b,3b}.npz)
+                   --tools/gen_interp.py -->  command stream interpreted by the sm_100a kernel
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import extract_pip  # noqa: E402
+import gen_interp  # noqa: E402
+
+DATA = os.path.join(ROOT, "mbpol_openmm_plugin_b200", "data")
+SPEC = {"pip2b": (31, 1153, 12725, "2"), "pip3b": (36, 1163, 33525, "3")}
+
+
+@pytest.mark.parametrize("name", ["pip2b", "pip3b"])
+def test_table_shape(name):
+    t = dict(np.load(os.path.join(DATA, name + ".npz")))
+    nv, nc, nm, _ = SPEC[name]
+    assert int(t["n_vars"]) == nv and len(t["coef"]) == nc and len(t["mono_coef"]) == nm
+    assert set(np.unique(t["mono_coef"]).tolist()) == set(range(nc))      # every coefficient is used
+    deg = (t["mono_vars"] != 255).sum(axis=1)
+    assert deg.min() >= 1 and deg.max() == 4
+
+
+@pytest.mark.parametrize("name", ["pip2b", "pip3b"])
+def test_table_reproduces_reference_polynomial_values(name):
+    """golden values were produced by poly_2b_v6x_eval / poly_3b_v2x::eval (tests/golden/make_golden.py)"""
+    t = dict(np.load(os.path.join(DATA, name + ".npz")))
+    g = np.load(os.path.join(GOLDEN, "poly_values.npz"))
+    k = SPEC[name][3]
+    for x, e, grad in zip(g["x" + k], g["e" + k], g["g" + k]):
+        E, G = extract_pip.eval_table(t, x)
+        assert abs(E - e) <= 1e-12 * max(1.0, abs(e))
+        assert np.abs(G - grad).max() <= 1e-12 * np.abs(grad).max()
+
+
+@pytest.mark.parametrize("name", ["pip2b", "pip3b"])
+def test_command_stream_matches_table(name, tmp_path):
+    """python interpreter of the packed stream (same records the GPU kernel executes) vs the monomial definition"""
+    meta, words = gen_interp.generate(name, str(tmp_path))
+    t = dict(np.load(os.path.join(DATA, name + ".npz")))
+    rng = np.random.default_rng(11)
+    for _ in range(2):
+        x = rng.uniform(0.05, 1.6, int(t["n_vars"]))
+        E, G = gen_interp.interpret(name, words, x, meta["chunk_bytes"])
+        Er, Gr = extract_pip.eval_table(t, x)
+        assert abs(E - Er) <= 1e-13 * max(1.0, abs(Er))
+        assert np.abs(G - Gr).max() <= 1e-13 * np.abs(Gr).max()
+    # stream layout invariants the kernel relies on
+    cw = meta["chunk_bytes"] // 8
+    assert len(words) % cw == 0 and not words[-cw:].any()               # trailing all-zero look-ahead chunk
+    assert meta["smem_bytes"] <= 227 * 1024
+
+
+def test_port_polynomial_matches_table(port):
+    for order, name in ((2, "pip2b"), (3, "pip3b")):
+        t = dict(np.load(os.path.join(DATA, name + ".npz")))
+        x = np.random.default_rng(5).uniform(0.1, 1.4, int(t["n_vars"]))
+        E, G = port.poly(order, x)
+        Er, Gr = extract_pip.eval_table(t, x)
+        assert abs(E - Er) <= 1e-12 * abs(Er) and np.abs(G - Gr).max() <= 1e-12 * np.abs(Gr).max()

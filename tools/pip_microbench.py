@@ -49,13 +49,23 @@ def ptx_block(cubin, default):
     return default
 
 
+def load_meta(cubin):
+    import json as _json
+    p = os.path.join(os.path.dirname(cubin), os.path.basename(cubin)[:5] + "_meta.json")
+    return _json.load(open(p)) if os.path.exists(p) else {}
+
+
 def run(cubin, waves, block, reps, ref):
     name = os.path.basename(cubin)[:5]
     block = ptx_block(cubin, block)
+    meta = load_meta(cubin)
+    smem = int(meta.get("smem_bytes", 0))
     nv = N_VARS[name]
     data = np.fromfile(cubin, dtype=np.uint8)
     mod = ck(cu.cuModuleLoadData(data.ctypes.data))
     fn = ck(cu.cuModuleGetFunction(mod, f"{name}_eval".encode()))
+    if smem:
+        ck(cu.cuFuncSetAttribute(fn, cu.CUfunction_attribute.CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem))
     n = 148 * 256 * waves
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(nv, n, dtype=torch.float64, device="cuda", generator=g) * 1.2 + 0.1
@@ -67,7 +77,7 @@ def run(cubin, waves, block, reps, ref):
     grid = (n + block - 1) // block
 
     def launch():
-        ck(cu.cuLaunchKernel(fn, grid, 1, 1, block, 1, 1, 0, stream, argp.ctypes.data, 0))
+        ck(cu.cuLaunchKernel(fn, grid, 1, 1, block, 1, 1, smem, stream, argp.ctypes.data, 0))
 
     for _ in range(3):
         launch()
@@ -81,7 +91,7 @@ def run(cubin, waves, block, reps, ref):
     ms = e0.elapsed_time(e1) / reps
     res = {"cubin": cubin, "n": n, "block": block, "ms": round(ms, 4), "tuples_per_s": n / ms * 1e3,
            "alg_tflops": n * ALG_FLOP[name] / ms / 1e9}
-    ni = fp64_instr(cubin)
+    ni = meta.get("fp64_instr") or fp64_instr(cubin)
     if ni:
         res["fp64_instr"] = ni
         # B200: 148 SM x 64 lanes -> 148*2 warp-instructions per clock
