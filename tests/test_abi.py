@@ -60,3 +60,19 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "refbind" not in src and "liboracle" not in src and "libmbpol_ref" not in src, fn
+
+
+def test_plain_c_client_compiles_and_links(tmp_path):
+    """examples/capi_demo.c: the ABI is usable from plain C (no C++/torch types in the signatures)"""
+    import subprocess
+    from mbpol_openmm_plugin_b200 import _lib
+    exe = str(tmp_path / "capi_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "examples", "capi_demo.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lmbpol_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if has_cuda():
+        assert r.returncode == 0 and "E_2B = 6.142078" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stderr
