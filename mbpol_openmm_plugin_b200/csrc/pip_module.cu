@@ -29,9 +29,11 @@ struct DriverApi {
     bool ok = false;
 };
 
+constexpr int MAX_KERN = 4;     // variable-class kernels per polynomial (partial values / gradients accumulate)
 struct DeviceModule {
     CUmodule mod2 = nullptr, mod3 = nullptr;
-    CUfunction fn2 = nullptr, fn3 = nullptr;
+    CUfunction fn2[MAX_KERN] = {}, fn3[MAX_KERN] = {};
+    bool ready = false;
 };
 
 std::mutex g_mu;
@@ -65,19 +67,23 @@ int ensure_loaded(int dev, std::string* err) {
         g_api.ok = true;
     }
     DeviceModule& m = g_dev[dev];
-    if (m.fn3) return MBPOL_OK;
+    if (m.ready) return MBPOL_OK;
+    static_assert(PIP2B_NKERN <= MAX_KERN && PIP3B_NKERN <= MAX_KERN, "too many class kernels");
     cudaFree(0);   // make the primary context of the current device current for the driver calls below
     CUresult r;
-    if ((r = g_api.moduleLoadData(&m.mod2, pip2b_cubin)) != CUDA_SUCCESS ||
-        (r = g_api.moduleLoadData(&m.mod3, pip3b_cubin)) != CUDA_SUCCESS ||
-        (r = g_api.moduleGetFunction(&m.fn2, m.mod2, "pip2b_eval")) != CUDA_SUCCESS ||
-        (r = g_api.moduleGetFunction(&m.fn3, m.mod3, "pip3b_eval")) != CUDA_SUCCESS ||
-        (r = g_api.funcSetAttribute(m.fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP2B_SMEM)) != CUDA_SUCCESS ||
-        (r = g_api.funcSetAttribute(m.fn3, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP3B_SMEM)) != CUDA_SUCCESS) {
+    if ((r = g_api.moduleLoadData(&m.mod2, pip2b_cubin)) == CUDA_SUCCESS) r = g_api.moduleLoadData(&m.mod3, pip3b_cubin);
+    for (int k = 0; r == CUDA_SUCCESS && k < PIP2B_NKERN; ++k)
+        if ((r = g_api.moduleGetFunction(&m.fn2[k], m.mod2, PIP2B_ENTRIES[k])) == CUDA_SUCCESS)
+            r = g_api.funcSetAttribute(m.fn2[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP2B_SMEM);
+    for (int k = 0; r == CUDA_SUCCESS && k < PIP3B_NKERN; ++k)
+        if ((r = g_api.moduleGetFunction(&m.fn3[k], m.mod3, PIP3B_ENTRIES[k])) == CUDA_SUCCESS)
+            r = g_api.funcSetAttribute(m.fn3[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, PIP3B_SMEM);
+    if (r != CUDA_SUCCESS) {
         if (err) *err = "loading the sm_100a PIP cubins failed: " + cu_msg(r);
         m = DeviceModule();
         return MBPOL_ECUDA;
     }
+    m.ready = true;
     return MBPOL_OK;
 }
 
@@ -102,17 +108,21 @@ int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, c
     }
     int rc = ensure_loaded(dev, err);
     if (rc != MBPOL_OK) return rc;
-    unsigned un = (unsigned)n, uld = (unsigned)ld;
-    void* args[] = {(void*)&x, (void*)&out, (void*)&un, (void*)&uld};
+    unsigned un = (unsigned)n, uld = (unsigned)ld, acc = 0;
+    void* args[] = {(void*)&x, (void*)&out, (void*)&un, (void*)&uld, (void*)&acc};
     const unsigned block = order == 2 ? PIP2B_BLOCK : PIP3B_BLOCK, smem = order == 2 ? PIP2B_SMEM : PIP3B_SMEM;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    CUresult r = g_api.launchKernel(order == 2 ? g_dev[dev].fn2 : g_dev[dev].fn3, grid, 1, 1, block, 1, 1, smem,
-                                    (CUstream)s, args, nullptr);
-    if (r != CUDA_SUCCESS) {
-        if (err) *err = "launch of the PIP kernel failed: " + cu_msg(r);
-        return MBPOL_ECUDA;
+    const int nk = order == 2 ? PIP2B_NKERN : PIP3B_NKERN;
+    for (int k = 0; k < nk; ++k) {      // class kernels: the first overwrites `out`, the others accumulate into it
+        acc = k > 0;
+        CUresult r = g_api.launchKernel(order == 2 ? g_dev[dev].fn2[k] : g_dev[dev].fn3[k], grid, 1, 1, block, 1, 1, smem,
+                                        (CUstream)s, args, nullptr);
+        if (r != CUDA_SUCCESS) {
+            if (err) *err = "launch of the PIP kernel failed: " + cu_msg(r);
+            return MBPOL_ECUDA;
+        }
+        MBPOL_COUNT_LAUNCH(1);
     }
-    MBPOL_COUNT_LAUNCH(1);
     return MBPOL_OK;
 }
 

@@ -65,50 +65,102 @@ def build_tree(monos, var=None):
     return node
 
 
-def serialise(name, tab, fuse=True):
-    """-> (records, masks).  records: list of (opcode, k, payload doubles); masks: list of block-index tuples."""
+def serialise(name, tab, fuse=True, class_blocks=None, with_consts=True, npair=0):
+    """-> (records, masks).  records: list of (opcode, k, payload doubles); masks: list of block-index tuples.
+
+    ``class_blocks`` restricts the program to the leaves whose variable lies in those blocks (the polynomial is linear in
+    its leaf sums, so the classes' partial values and gradients simply add); ``with_consts`` says whether this class
+    also carries the monomials that end at an inner node."""
     blocks = BLOCKS[name]
+    use = list(range(len(blocks))) if class_blocks is None else list(class_blocks)
+    cvars = set(v for b in use for v in blocks[b])
     coef = tab["coef"]
     monos = [(tuple(int(v) for v in row if v != PAD), int(c)) for row, c in zip(tab["mono_vars"], tab["mono_coef"])]
     root = build_tree(monos)
     freq = collections.Counter()
+    keep = {}
+
+    def has(node):
+        r = keep.get(id(node))
+        if r is None:
+            r = any(v in cvars for v in node.leaves) or (with_consts and node.const is not None)
+            for k in node.kids:
+                r = has(k) or r
+            keep[id(node)] = r
+        return r
+
+    def leaves_of(node):
+        return {v: c for v, c in node.leaves.items() if v in cvars}
 
     def mask_of(node):
-        return tuple(b for b, blk in enumerate(blocks) if any(v in node.leaves for v in blk))
+        return tuple(b for b in use if any(v in node.leaves for v in blocks[b]))
 
     def count(node):
-        if node.leaves:
+        if leaves_of(node):
             freq[mask_of(node)] += 1
         for k in node.kids:
-            count(k)
+            if has(k):
+                count(k)
+    has(root)
     count(root)
     masks = [m for m, _ in freq.most_common()]
     mask_id = {m: i for i, m in enumerate(masks)}
     recs = []
 
+    def const_of(node):
+        return coef[node.const] if (with_consts and node.const is not None) else 0.0
+
     def emit(node, depth):
         assert depth <= MAX_DEPTH
-        if depth > 0 and not node.kids and node.leaves and fuse:
+        lv = leaves_of(node)
+        kids = [k for k in node.kids if has(k)]
+        # evaluation order of siblings is free: group the childless ones by mask so that equal records are adjacent
+        def order(k):
+            childless = not any(has(q) for q in k.kids) and bool(leaves_of(k))
+            return (0, mask_id[mask_of(k)]) if childless else (1, 0)
+        kids.sort(key=order)
+        if depth > 0 and not kids and lv and fuse:
             m = mask_of(node)
-            payload = [coef[node.const] if node.const is not None else 0.0]
-            payload += [coef[node.leaves[v]] if v in node.leaves else 0.0 for b in m for v in blocks[b]]
+            payload = [const_of(node)] + [coef[lv[v]] if v in lv else 0.0 for b in m for v in blocks[b]]
             recs.append((OP_MASK + len(masks) + mask_id[m], node.var, payload))
             return
         if depth > 0:
-            recs.append((OP_ENTER + depth - 1, node.var, [coef[node.const] if node.const is not None else 0.0]))
+            recs.append((OP_ENTER + depth - 1, node.var, [const_of(node)]))
         else:
             assert node.const is None
-        if node.leaves:
+        if lv:
             m = mask_of(node)
-            payload = [coef[node.leaves[v]] if v in node.leaves else 0.0 for b in m for v in blocks[b]]
+            payload = [coef[lv[v]] if v in lv else 0.0 for b in m for v in blocks[b]]
             recs.append((OP_MASK + mask_id[m], 0, payload))
-        for k in node.kids:
+        for k in kids:
             emit(k, depth + 1)
         if depth > 0:
             recs.append((OP_LEAVE + depth - 1, node.var, []))
     emit(root, 0)
     recs.append((OP_END, 0, []))
+    if npair:
+        # PAIR_m = two consecutive LEAFNODE_m records evaluated by one handler with interleaved, independent chains
+        pairable = pair_masks(name, masks, npair)
+        nm, merged, i = len(masks), [], 0
+        while i < len(recs):
+            op, k, pl = recs[i]
+            m = op - OP_MASK - nm
+            if m in pairable and i + 1 < len(recs) and recs[i + 1][0] == op:
+                merged.append((OP_MASK + 2 * nm + pairable.index(m), k | (recs[i + 1][1] << 8),
+                               list(pl) + list(recs[i + 1][2])))
+                i += 2
+            else:
+                merged.append(recs[i])
+                i += 1
+        recs = merged
     return recs, masks
+
+
+def pair_masks(name, masks, npair, max_slots=18):
+    """mask ids (most frequent first) that get a PAIR handler: small enough that two payloads fit the register budget"""
+    blocks = BLOCKS[name]
+    ok = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= max_slots]
+    return ok[:npair]
 
 
 def rec_words(n_payload):
@@ -141,7 +193,7 @@ def pack(recs, chunk_bytes):
     return np.array([w for c in chunks for w in c], dtype=np.uint64)
 
 
-def interpret(name, words, x, chunk_bytes):
+def interpret(name, words, x, chunk_bytes, masks=None):
     """numpy/python reference interpreter of the packed stream (used by the CPU tests)."""
     cw = chunk_bytes // 8
     blocks = BLOCKS[name]
@@ -150,7 +202,7 @@ def interpret(name, words, x, chunk_bytes):
     x = np.asarray(x, dtype=np.float64)
     g = np.zeros(nv)
     f = words.view(np.float64)
-    masks = interpret.masks[name]
+    masks = interpret.masks[name] if masks is None else masks
     pc = 1
     v, a = 0.0, 1.0
     stack = []
@@ -184,21 +236,28 @@ def interpret(name, words, x, chunk_bytes):
                     v += c * x[j]
                     g[j] += c * a
             pc += 1 + (n if n % 2 else n + 1)
-        else:                                   # fused leaf node: ENTER k, const; MASK_m; LEAVE k
-            m = masks[op - OP_MASK - len(masks)]
-            a2 = a * x[k]
-            u = f[pc + 1]
-            q = pc + 2
-            n = 1
-            for b in m:
-                for j in blocks[b]:
-                    c = f[q]
-                    q += 1
-                    n += 1
-                    u += c * x[j]
-                    g[j] += c * a2
-            v += x[k] * u
-            g[k] += a * u
+        else:                                   # fused leaf node(s): ENTER k, const; MASK_m; LEAVE k  (x2 for PAIR_m)
+            pair = op >= OP_MASK + 2 * len(masks)
+            if pair:
+                m = masks[pair_masks(name, masks, 1 << 30)[op - OP_MASK - 2 * len(masks)]]
+            else:
+                m = masks[op - OP_MASK - len(masks)]
+            q = pc + 1
+            n = 0
+            for kk in ((k & 0xFF, k >> 8) if pair else (k,)):
+                a2 = a * x[kk]
+                u = f[q]
+                q += 1
+                n += 1
+                for b in m:
+                    for j in blocks[b]:
+                        c = f[q]
+                        q += 1
+                        n += 1
+                        u += c * x[j]
+                        g[j] += c * a2
+                v += x[kk] * u
+                g[kk] += a * u
             pc += 1 + (n if n % 2 else n + 1)
 
 
@@ -209,41 +268,40 @@ def hexd(v):
     return "0d%016X" % struct.unpack("<Q", struct.pack("<d", float(v)))[0]
 
 
-def to_ptx(name, words, masks, nv, block=256, min_blocks=1, nacc=2, ahead=4):
-    """PTX module: the command stream as initialised .global data plus the interpreter kernel
+def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
+               opaque=True, cmem=False, repeat=1, npair=0):
+    """One interpreter kernel
 
-        {name}_eval(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld)
+        {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
 
-    One thread per tuple, x / g / adjoints in registers.  The stream is staged through a double-buffered shared-memory
-    window: every thread fetches 16 bytes of chunk c+1 into registers when chunk c starts, stores them when chunk c
-    ends (OP_NEXT) and one bar.sync flips the buffers -- the global-load latency is never exposed, the handlers read
-    coefficients with broadcast ld.shared (every lane the same address)."""
+    One thread per tuple; x / g of the class variables and the adjoints in registers.  The stream is staged through a
+    double-buffered shared-memory window: every thread fetches `piece` bytes of chunk c+1 into registers when chunk c
+    starts, stores them when chunk c ends (OP_NEXT) and one bar.sync flips the buffers -- the global-load latency is
+    never exposed, the handlers read coefficients with broadcast ld.shared (every lane the same address).
+    Returns (lines, dynamic shared bytes)."""
     blocks = BLOCKS[name]
     NT = block
-    CH = NT * 16                       # chunk bytes = one 16-byte piece per thread
+    CH = NT * piece                    # chunk bytes = one piece per thread
+    # EXPERIMENT (cmem=True): the whole stream sits in the constant bank (<= 64 KB) and is read with uniform ld.const;
+    # no shared-memory staging, no OP_NEXT.  `repeat` re-runs the stream (timing experiments with truncated streams).
+    LD, SP, SPV = ("ld.const", "%cp", "%cp") if cmem else ("ld.shared", "%sp", "%spv")
+    cset = set(class_vars)
+    pfld = "ld.global.nc.v2.f64 {%pf0, %pf1}" if piece == 16 else "ld.global.nc.f64 %pf0"
+    pfst = "{%pf0, %pf1}" if piece == 16 else "%pf0"
+    pfty = "v2.f64" if piece == 16 else "f64"
     SX, SG, SB = 0, nv * NT * 8, 2 * nv * NT * 8       # smem: x copy | g accumulators | 2 stream buffers
     out = []
     w = out.append
-    w("// GENERATED by tools/gen_interp.py -- command-stream adjoint-Horner PIP evaluator (see the tool's docstring).")
-    w(".version 8.7")
-    w(".target sm_100a")
-    w(".address_size 64")
-    w("")
-    w(f".global .align 16 .b64 {name}_stream[{len(words)}] = {{")
-    for i in range(0, len(words), 8):
-        w(", ".join("0x%016X" % int(v) for v in words[i:i + 8]) + ("," if i + 8 < len(words) else ""))
-    w("};")
-    w(".extern .shared .align 16 .b8 pip_smem[];")
-    w("")
-    w(f".visible .entry {name}_eval(.param .u64 p_x, .param .u64 p_out, .param .u32 p_n, .param .u32 p_ld)")
+    w(f".visible .entry {entry}(.param .u64 p_x, .param .u64 p_out, .param .u32 p_n, .param .u32 p_ld, .param .u32 p_acc)")
     w(f".maxntid {NT}, 1, 1")
     w(f".minnctapersm {min_blocks}")
     w("{")
-    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<32>, %vc, %vd, %ac, %w, %cst, %gk, %one, %u0, %u1, %a0, %xk0, %pf0, %pf1, %n<6>, %u2, %u3;")
+    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<64>, %vc, %vd, %ac, %w, %cst, %gk, %one, %u0, %u1, %a0, %xk0, %pf0, %pf1, %n<6>, %u2, %u3;")
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
-    w(".reg .u32 %sp, %bufcur, %bufoth, %mine;")
-    w(".reg .pred %valid;")
+    w(".reg .u32 %sp, %spv, %z, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %a1, %xkb, %gkb;")
+    w(".reg .pred %valid, %pacc; .reg .u32 %acc;")
+    w("ld.param.u32 %acc, [p_acc]; setp.ne.u32 %pacc, %acc, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
     w("cvta.to.global.u64 %px, %px; cvta.to.global.u64 %po, %po;")
     w("mov.u32 %r0, %ctaid.x; mov.u32 %r1, %ntid.x; mov.u32 %r2, %tid.x;")
@@ -256,56 +314,78 @@ def to_ptx(name, words, masks, nv, block=256, min_blocks=1, nacc=2, ahead=4):
     w("shl.b32 %sx, %r2, 3; add.u32 %sx, %sx, %r3;")             # &xs[0][tid]
     w(f"add.u32 %sg, %sx, {SG};")                                  # &gs[0][tid]
     w(f"add.u32 %bufcur, %r3, {SB}; add.u32 %bufoth, %bufcur, {CH};")
-    w("shl.b32 %mine, %r2, 4;")                                    # this thread's 16-byte piece of a chunk
+    w(f"mul.lo.u32 %mine, %r2, {piece};")                           # this thread's piece of a chunk
     # stream chunk 0 -> buffer 0, chunk 1 -> registers
-    w(f"mov.u64 %gs, {name}_stream; cvta.to.global.u64 %gs, %gs; cvt.u64.u32 %off, %mine; add.u64 %gs, %gs, %off;")
-    w("ld.global.nc.v2.f64 {%pf0, %pf1}, [%gs];")
-    w("add.u32 %addr, %bufcur, %mine; st.shared.v2.f64 [%addr], {%pf0, %pf1};")
-    w(f"add.u64 %gs, %gs, {CH}; ld.global.nc.v2.f64 {{%pf0, %pf1}}, [%gs];")
+    w(f"mov.u64 %gs, {stream}; cvta.to.global.u64 %gs, %gs; cvt.u64.u32 %off, %mine; add.u64 %gs, %gs, %off;")
+    w(f"{pfld}, [%gs];")
+    w(f"add.u32 %addr, %bufcur, %mine; st.shared.{pfty} [%addr], {pfst};")
+    w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
     w("mov.f64 %one, 0d3FF0000000000000;")
+    if opaque:
+        # word 0 of the stream is padding (zero).  Reading one of its halves at a thread-dependent address gives a zero
+        # ptxas cannot prove uniform: payload loads through %spv = %sp + 0 then stay in vector registers instead of
+        # being moved to uniform registers one R2UR per 32 bits (580 R2UR vs 2135 DFMA in the static SASS otherwise).
+        w(f"mov.u64 %off, {stream}; cvta.to.global.u64 %off, %off; and.b32 %r3, %r2, 1; mul.wide.u32 %ldb, %r3, 4;")
+        w("add.u64 %off, %off, %ldb; ld.global.nc.u32 %z, [%off]; mul.wide.u32 %ldb, %ld, 8;")
+    else:
+        w("mov.u32 %z, 0;")
     for i in range(nv):
         w(f"ld.global.nc.f64 %x{i}, [%px]; add.u64 %px, %px, %ldb;")
     for i in range(nv):
         w(f"st.shared.f64 [%sx+{i * NT * 8}], %x{i}; st.shared.f64 [%sg+{i * NT * 8}], 0d0000000000000000;")
-        w(f"mov.f64 %g{i}, 0d0000000000000000;")
+        if i in cset:
+            w(f"mov.f64 %g{i}, 0d0000000000000000;")
     w("mov.f64 %vc, 0d0000000000000000; mov.f64 %vd, 0d0000000000000000; mov.f64 %ac, %one;")
     w("bar.sync 0;")
-    w("add.u32 %sp, %bufcur, 8;")
-    n_ops = OP_MASK + 2 * len(masks)
+    w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
+    n_ops = OP_MASK + 2 * len(masks) + (len(pair_masks(name, masks, npair)) if npair else 0)
     NPRE = 6                                   # payload words of the NEXT record pre-loaded by every handler
     w("TBL: .branchtargets " + ", ".join(f"H{i}" for i in range(n_ops)) + ";")
 
     def preload(byte_off):
         """first NPRE payload words of the record at %sp+byte_off -> %n0..%n5 (garbage past short records: unused)"""
         for q in range(0, NPRE, 2):
-            w(f"ld.shared.v2.f64 {{%n{q}, %n{q + 1}}}, [%sp+{byte_off + 8 + 8 * q}];")
+            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{byte_off + 8 + 8 * q}];")
 
     def head(nwords):
         """current k <- header fetched by the previous handler; fetch the next header"""
         w("mov.u32 %k, %nk;")
-        w(f"ld.shared.v2.u32 {{%nop, %nk}}, [%sp+{8 * nwords}];")
+        w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}+{8 * nwords}];")
 
     def tail(nwords):
         preload(8 * nwords)
-        w(f"add.u32 %sp, %sp, {8 * nwords};")
+        if cmem:
+            w(f"add.u64 %cp, %cp, {8 * nwords};")
+        else:
+            w(f"add.u32 %sp, %sp, {8 * nwords}; add.u32 %spv, %spv, {8 * nwords};")
         w("brx.idx %nop, TBL;")                 # per-handler dispatch: ptxas can hoist the jump-table read
 
+    FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
+
     def coef(i):
+        if FAKE:
+            return f"%n{i % NPRE}"
         return f"%n{i}" if i < NPRE else f"%c{i - NPRE}"
 
-    w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
+    if cmem:
+        w(f".reg .u64 %cp; .reg .u32 %rep; .reg .pred %prep; mov.u32 %rep, {repeat};")
+        w("RESTART:")
+        w(f"mov.u64 %cp, {stream}; add.u64 %cp, %cp, 8;")
+    w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}];")
     preload(0)
     w("brx.idx %nop, TBL;")
     # ---- END
     w(f"H{OP_END}:")
+    if cmem:
+        w("sub.u32 %rep, %rep, 1; setp.ne.u32 %prep, %rep, 0; @%prep bra.uni RESTART;")
     w("bra.uni FINISH;")
     # ---- NEXT: publish chunk c+1 (held in registers since chunk c began), flip buffers, start fetching chunk c+2
     w(f"H{OP_NEXT}:")
-    w("add.u32 %addr, %bufoth, %mine; st.shared.v2.f64 [%addr], {%pf0, %pf1};")
+    w(f"add.u32 %addr, %bufoth, %mine; st.shared.{pfty} [%addr], {pfst};")
     w("bar.sync 0;")
     w("mov.u32 %addr, %bufcur; mov.u32 %bufcur, %bufoth; mov.u32 %bufoth, %addr;")
-    w(f"add.u64 %gs, %gs, {CH}; ld.global.nc.v2.f64 {{%pf0, %pf1}}, [%gs];")
-    w("add.u32 %sp, %bufcur, 8;")
+    w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
+    w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
     preload(0)
     w("brx.idx %nop, TBL;")
@@ -343,11 +423,11 @@ def to_ptx(name, words, masks, nv, block=256, min_blocks=1, nacc=2, ahead=4):
         if fused:
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
-        for i in range(NPRE, n, 2):                        # the rest of this record's payload
+        for i in range(NPRE, n if not FAKE else 0, 2):     # the rest of this record's payload
             if i + 1 < n:
-                w(f"ld.shared.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [%sp+{8 + 8 * i}];")
+                w(f"{LD}.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [{SPV}+{8 + 8 * i}];")
             else:
-                w(f"ld.shared.f64 {coef(i)}, [%sp+{8 + 8 * i}];")
+                w(f"{LD}.f64 {coef(i)}, [{SPV}+{8 + 8 * i}];")
         assert n - NPRE <= 32
         if fused:
             acc, adj = [f"%u{q}" for q in range(max(1, nacc))], "%a0"
@@ -407,57 +487,164 @@ def to_ptx(name, words, masks, nv, block=256, min_blocks=1, nacc=2, ahead=4):
             w(op)
         tail(nwords)
 
+    def pair_handler(label, m):
+        """two LEAFNODE_m records at once: A accumulates on %u0/%u1 -> %vc, B on %u2/%u3 -> %vd"""
+        w(f"{label}:")
+        vars_ = [j for b in m for j in blocks[b]]
+        n1 = 1 + len(vars_)
+        n = 2 * n1
+        nwords = rec_words(n)
+        head(nwords)
+        w("and.b32 %ka, %k, 255; shr.u32 %kb, %k, 8;")
+        w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
+        w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
+        w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
+        w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sg; ld.shared.f64 %gkb, [%addrb];")
+        for i in range(NPRE, n, 2):
+            if i + 1 < n:
+                w(f"{LD}.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [{SPV}+{8 + 8 * i}];")
+            else:
+                w(f"{LD}.f64 {coef(i)}, [{SPV}+{8 + 8 * i}];")
+        assert n - NPRE <= 48
+        seq = {}
+        for tag, base, accs, adj in (("A", 0, ["%u0", "%u1"], "%a0"), ("B", n1, ["%u2", "%u3"], "%a1")):
+            vops, gops = [f"mov.f64 {accs[0]}, {coef(base)};"], []
+            started = {accs[0]}
+            for i, j in enumerate(vars_):
+                c = coef(base + 1 + i)
+                a = accs[(i + 1) % 2]
+                if a in started:
+                    vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
+                else:
+                    vops.append(f"mul.rn.f64 {a}, {c}, %x{j};")
+                    started.add(a)
+                gops.append(f"fma.rn.f64 %g{j}, {c}, {adj}, %g{j};")
+            seq[tag] = (vops, gops, len(started) > 1)
+        for a_op, b_op in zip(seq["A"][0], seq["B"][0]):
+            w(a_op)
+            w(b_op)
+        w("mul.rn.f64 %a0, %ac, %xk0;")
+        w("mul.rn.f64 %a1, %ac, %xkb;")
+        if seq["A"][2]:
+            w("add.rn.f64 %u0, %u0, %u1;")
+            w("add.rn.f64 %u2, %u2, %u3;")
+        rops = ["fma.rn.f64 %vc, %xk0, %u0, %vc;", "fma.rn.f64 %vd, %xkb, %u2, %vd;",
+                "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u2, %gkb;",
+                "st.shared.f64 [%addr], %gk;", "st.shared.f64 [%addrb], %gkb;"]
+        gops = [op for pair in zip(seq["A"][1], seq["B"][1]) for op in pair]
+        gap = max(1, len(gops) // (len(rops) + 1))
+        gi = 0
+        for r in rops:
+            for _ in range(gap):
+                if gi < len(gops):
+                    w(gops[gi])
+                    gi += 1
+            w(r)
+        for op in gops[gi:]:
+            w(op)
+        tail(nwords)
+
     for mi, m in enumerate(masks):
         block_handler(f"H{OP_MASK + mi}", m, False)
     for mi, m in enumerate(masks):
         block_handler(f"H{OP_MASK + len(masks) + mi}", m, True)
+    pairable = pair_masks(name, masks, npair) if npair else []
+    for pi, mi in enumerate(pairable):
+        pair_handler(f"H{OP_MASK + 2 * len(masks) + pi}", masks[mi])
     # ---- epilogue
     w("FINISH:")
     w("@!%valid bra DONE;")
     w("add.rn.f64 %vc, %vc, %vd;")
     w("mul.wide.u32 %off, %t, 8; add.u64 %po, %po, %off;")
+    w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %vc, %vc, %w;")
     w("st.global.f64 [%po], %vc; add.u64 %po, %po, %ldb;")
     for i in range(nv):
-        w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}]; add.rn.f64 %g{i}, %g{i}, %gk;")
-        w(f"st.global.f64 [%po], %g{i}; add.u64 %po, %po, %ldb;")
+        w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
+        if i in cset:
+            w(f"add.rn.f64 %gk, %gk, %g{i};")
+        w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
+        w("st.global.f64 [%po], %gk; add.u64 %po, %po, %ldb;")
     w("DONE:")
     w("ret;")
     w("}")
     return out, SB + 2 * CH
 
 
-def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True):
-    tab = dict(np.load(os.path.join(DATA, name + ".npz")))
-    nv = int(tab["n_vars"])
-    recs, masks = serialise(name, tab, fuse)
-    chunk = block * 16
-    words = pack(recs, chunk)
-    interpret.masks[name] = masks
-    blocks = BLOCKS[name]
+CLASSES = {            # block ids per class kernel (None = one kernel with every block)
+    "pip3b": {1: None, 2: [[1, 2, 3, 4], [0, 5, 6, 7, 8]], 3: [[2, 3, 4], [5, 6, 7], [0, 1, 8]]},
+    "pip2b": {1: None, 2: [[0, 1, 2, 3, 4], [5, 6, 7, 8, 9]]},
+}
+
+
+def count_fp64(recs, masks, blocks):
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
-        if op >= OP_MASK + len(masks):
+        if op >= OP_MASK + 2 * len(masks):
+            pm = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= 18]
+            n_fp += 2 * (2 * sum(len(blocks[b]) for b in masks[pm[op - OP_MASK - 2 * len(masks)]]) + 4)
+            hist["pair"] += 1
+        elif op >= OP_MASK + len(masks):
             n_fp += 2 * sum(len(blocks[b]) for b in masks[op - OP_MASK - len(masks)]) + 4
             hist["leafnode"] += 1
         elif op >= OP_MASK:
             n_fp += 2 * sum(len(blocks[b]) for b in masks[op - OP_MASK])
             hist["mask"] += 1
+        elif op == OP_NEXT:
+            pass
         elif op >= OP_LEAVE:
             n_fp += 3
             hist["leave"] += 1
         elif op >= OP_ENTER:
             n_fp += 1
             hist["enter"] += 1
-    ptx, smem = to_ptx(name, words, masks, nv, block, min_blocks, nacc, ahead)
+    return n_fp, hist
+
+
+def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
+             npair=0):
+    """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
+    Returns (meta, [(words, masks) per class])."""
+    tab = dict(np.load(os.path.join(DATA, name + ".npz")))
+    nv = int(tab["n_vars"])
+    blocks = BLOCKS[name]
+    classes = CLASSES[name][n_classes] or [list(range(len(blocks)))]
+    chunk = block * piece
+    lines = ["// GENERATED by tools/gen_interp.py -- command-stream adjoint-Horner PIP evaluator (see the tool's docstring).",
+             ".version 8.7", ".target sm_100a", ".address_size 64", "", ".extern .shared .align 16 .b8 pip_smem[];", ""]
+    streams, kernels = [], []
+    n_fp = 0
+    hist = collections.Counter()
+    smem = 0
+    for ci, cb in enumerate(classes):
+        recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair)
+        words = pack(recs, chunk)
+        f, h = count_fp64(recs, masks, blocks)
+        n_fp += f
+        hist.update(h)
+        sym = f"{name}_stream{ci}"
+        lines.append(f".global .align 16 .b64 {sym}[{len(words)}] = {{")
+        for i in range(0, len(words), 8):
+            lines.append(", ".join("0x%016X" % int(v) for v in words[i:i + 8]) + ("," if i + 8 < len(words) else ""))
+        lines.append("};")
+        cvars = sorted(v for b in cb for v in blocks[b])
+        entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
+        kl, sm = kernel_ptx(name, entry, sym, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
+                            npair=npair)
+        lines += [""] + kl
+        smem = max(smem, sm)
+        streams.append((words, masks))
+        kernels.append({"entry": entry, "vars": len(cvars), "masks": len(masks), "stream_bytes": int(words.nbytes),
+                        "fp64_instr": f})
+    interpret.masks[name] = streams[0][1]
     os.makedirs(out_dir, exist_ok=True)
-    with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as f:
-        f.write("\n".join(ptx) + "\n")
+    with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
     meta = {"name": name, "block": block, "smem_bytes": smem, "fp64_instr": n_fp, "chunk_bytes": chunk,
-            "stream_bytes": int(words.nbytes), "records": dict(hist), "masks": len(masks), "kind": "interp"}
-    with open(os.path.join(out_dir, f"{name}_meta.json"), "w") as f:
-        json.dump(meta, f)
-    return meta, words
+            "records": dict(hist), "kernels": kernels, "kind": "interp"}
+    with open(os.path.join(out_dir, f"{name}_meta.json"), "w") as fh:
+        json.dump(meta, fh)
+    return meta, streams
 
 
 def main():
@@ -468,9 +655,14 @@ def main():
     ap.add_argument("--nacc", type=int, default=2)
     ap.add_argument("--ahead", type=int, default=4, help="16-byte coefficient pieces loaded ahead of their use")
     ap.add_argument("--no-fuse", action="store_true")
+    ap.add_argument("--classes3", type=int, default=1, help="variable classes (kernels) for the 3B polynomial")
+    ap.add_argument("--classes2", type=int, default=1)
+    ap.add_argument("--piece", type=int, default=16, choices=[8, 16], help="stream bytes each thread stages per chunk")
+    ap.add_argument("--npair", type=int, default=0, help="pair handlers for the N most frequent masks")
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
-        meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse)
+        meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse,
+                           args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair)
         print(meta)
 
 

@@ -63,21 +63,31 @@ def run(cubin, waves, block, reps, ref):
     nv = N_VARS[name]
     data = np.fromfile(cubin, dtype=np.uint8)
     mod = ck(cu.cuModuleLoadData(data.ctypes.data))
-    fn = ck(cu.cuModuleGetFunction(mod, f"{name}_eval".encode()))
-    if smem:
-        ck(cu.cuFuncSetAttribute(fn, cu.CUfunction_attribute.CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem))
+    entries = [k["entry"] for k in meta.get("kernels", [])] or [f"{name}_eval"]
+    fns = []
+    for ent in entries:
+        fn = ck(cu.cuModuleGetFunction(mod, ent.encode()))
+        if smem:
+            ck(cu.cuFuncSetAttribute(fn, cu.CUfunction_attribute.CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem))
+        fns.append(fn)
+    block = int(meta.get("block", block))
     n = 148 * 256 * waves
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(nv, n, dtype=torch.float64, device="cuda", generator=g) * 1.2 + 0.1
     out = torch.zeros(nv + 1, n, dtype=torch.float64, device="cuda")
-    args = (np.array([x.data_ptr()], dtype=np.uint64), np.array([out.data_ptr()], dtype=np.uint64),
-            np.array([n], dtype=np.uint32), np.array([n], dtype=np.uint32))
-    argp = np.array([a.ctypes.data for a in args], dtype=np.uint64)
+    argps = []
+    keep = []
+    for i in range(len(fns)):
+        args = (np.array([x.data_ptr()], dtype=np.uint64), np.array([out.data_ptr()], dtype=np.uint64),
+                np.array([n], dtype=np.uint32), np.array([n], dtype=np.uint32), np.array([1 if i else 0], dtype=np.uint32))
+        keep.append(args)
+        argps.append(np.array([a.ctypes.data for a in args], dtype=np.uint64))
     stream = torch.cuda.current_stream().cuda_stream
     grid = (n + block - 1) // block
 
     def launch():
-        ck(cu.cuLaunchKernel(fn, grid, 1, 1, block, 1, 1, smem, stream, argp.ctypes.data, 0))
+        for fn, argp in zip(fns, argps):
+            ck(cu.cuLaunchKernel(fn, grid, 1, 1, block, 1, 1, smem, stream, argp.ctypes.data, 0))
 
     for _ in range(3):
         launch()
