@@ -399,16 +399,27 @@ int mbpol_eval_tuples(int order, const double* pos_nm, int32_t n_mol, const int3
 }
 
 // ---- FP64 FMA-pipe peak ------------------------------------------------------------------------------------------
+// 16 independent accumulators per thread, g_i = fma(c_i, a, g_i): two fresh 64-bit register reads + one repeated operand,
+// the cheapest operand pattern for the register file (profiles/r01_dfma_operand_microbench.md: 0.91-0.99 of nominal;
+// three fresh operands issue only every 3rd cycle).  Inline PTX keeps the compiler from restructuring the loop.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
-    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
-    for (int i = 0; i < iters; ++i) {
+    double g[16], c[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            r0 = __fma_rn(r0, a, b); r1 = __fma_rn(r1, a, b); r2 = __fma_rn(r2, a, b); r3 = __fma_rn(r3, a, b);
-            r4 = __fma_rn(r4, a, b); r5 = __fma_rn(r5, a, b); r6 = __fma_rn(r6, a, b); r7 = __fma_rn(r7, a, b);
+    for (int i = 0; i < 16; ++i) {
+        g[i] = threadIdx.x + i;
+        c[i] = b + 1e-9 * (threadIdx.x & 3) + 1e-8 * i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(g[i]) : "d"(c[i]), "d"(a));
         }
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += g[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 int mbpol_measure_fp64_peak(double* tflops, double* ms_out) {
@@ -417,7 +428,7 @@ int mbpol_measure_fp64_peak(double* tflops, double* ms_out) {
     int dev = 0, sms = 0;
     CKC(cudaGetDevice(&dev));
     CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int blocks = sms * 8, threads = 256, iters = 4096;
+    const int blocks = sms * 8, threads = 256, iters = 4096;   // 16 warps per scheduler
     double* out = nullptr;
     CKC(cudaMalloc(&out, sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
@@ -426,7 +437,7 @@ int mbpol_measure_fp64_peak(double* tflops, double* ms_out) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0);
-        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-6);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1e-6, 0.999999);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
