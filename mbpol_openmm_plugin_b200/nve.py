@@ -10,8 +10,9 @@ MASS_O, MASS_H = 15.99943, 1.007947
 KB = 0.0083144626          # kJ/mol/K
 
 
-def masses(n_mol, xp=np):
-    return xp.asarray(np.tile([MASS_O, MASS_H, MASS_H], n_mol)[:, None])
+def masses(n_mol):
+    """(3 n_mol, 1) numpy array of atomic masses in amu (O, H, H per molecule)"""
+    return np.tile([MASS_O, MASS_H, MASS_H], n_mol)[:, None].copy()
 
 
 def maxwell_boltzmann(n_mol, temperature=300.0, seed=1234):

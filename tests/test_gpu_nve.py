@@ -35,13 +35,14 @@ def test_nve_100_steps_tracks_the_oracle(checker):
         return e2 + e3, f2 + f3
 
     pg, vg, log_g = nve.run(gpu_force, torch.as_tensor(pos0).cuda(), torch.as_tensor(vel0).cuda(),
-                            nve.masses(n, lambda a: torch.as_tensor(a).cuda()), steps)
+                            torch.as_tensor(nve.masses(n)).cuda(), steps)
     pc, vc, log_c = nve.run(cpu_force, pos0, vel0, nve.masses(n), steps)
     log_g, log_c = np.array(log_g), np.array(log_c)
     assert np.abs(pg.cpu().numpy() - pc).max() < 1e-10                  # nm, after `steps` steps
     assert np.abs(vg.cpu().numpy() - vc).max() < 1e-8                   # nm/ps
     assert np.abs(log_g[:, 0] - log_c[:, 0]).max() <= 1e-9 * np.abs(log_c[:, 0]).max()
-    etot = log_g.sum(axis=1)
-    # 2B+3B alone is not a complete force field (no intramolecular term), but it is conservative: velocity Verlet at
-    # 0.2 fs keeps the total energy to ~1e-6 relative over 20 fs
-    assert np.abs(etot - etot[0]).max() < 2e-5 * abs(etot[0])
+    # Total energy is NOT asserted to be conserved: the Reference platform's chain-triplet list drops a trimer the moment
+    # d(I,J) or d(J,K) crosses 4.5 A even when the other two switches are still non-zero (SURVEY.md finding 2), so the
+    # reference's own 2B+3B surface has small discontinuities.  What must hold is that both implementations see the same
+    # total energy along the same trajectory.
+    assert np.abs(log_g.sum(axis=1) - log_c.sum(axis=1)).max() <= 1e-9 * np.abs(log_c.sum(axis=1)).max()
