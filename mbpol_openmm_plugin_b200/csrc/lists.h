@@ -12,6 +12,7 @@ struct GridArg {
     double box[3];         // periodic box edges (nm)
     double lo[3];          // non-periodic: lower corner of the bounding box
     double inv_extent[3];
+    double inv_box[3];     // screening only (pair_d2_fast)
     int nc[3];             // cells per axis (cell edge >= largest cutoff)
     int periodic;
 };

@@ -70,6 +70,16 @@ __device__ __forceinline__ double f_switch(double r, double ri, double rf, doubl
     return 1.0;
 }
 
+// Per-tuple force blocks are W = 18 / 27 consecutive doubles: written straight from registers every lane would touch its
+// own 32-byte sectors (stride 144 / 216 B).  Stage the CTA's blocks in shared memory and stream them out contiguously.
+template <int W, int NT>
+__device__ __forceinline__ void store_blocks(double* __restrict__ f_out, int64_t cta_first, int64_t n, double (&sh)[NT * W]) {
+    __syncthreads();
+    const int64_t count = min((int64_t)NT, n - cta_first) * W;
+    double* dst = f_out + cta_first * W;
+    for (int64_t i = threadIdx.x; i < count; i += NT) dst[i] = sh[i];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 2B.  Sites: 0 Oa, 1 Ha1, 2 Ha2, 3 Ob, 4 Hb1, 5 Hb2, 6 Xa1, 7 Xa2, 8 Xb1, 9 Xb2 (Angstrom).
 // Variable table = MBPolReferenceTwoBodyForce.cpp:170-207.  kind 0: exp(k(r0-r)), 1: exp(k(r0-r))/r
@@ -155,19 +165,19 @@ __global__ void __launch_bounds__(128) dimer_forces_kernel(const double* __restr
                                                            const double* __restrict__ rinv,
                                                            const double* __restrict__ poly, double* __restrict__ e_out,
                                                            double* __restrict__ f_out) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int ma = pairs[2 * (first + t)], mb = pairs[2 * (first + t) + 1];
+    __shared__ double sh[128 * 18];
+    const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t t = cta_first + threadIdx.x;
+    double* f = sh + 18 * threadIdx.x;
     V3 s[10], dOO;
-    double rOO;
-    const bool active = dimer_sites(pos, idx, ma, mb, box, s, dOO, rOO);
-    double* f = f_out + 18 * (size_t)t;
+    double rOO = 0.0;
+    bool active = false;
+    if (t < n) active = dimer_sites(pos, idx, pairs[2 * (first + t)], pairs[2 * (first + t) + 1], box, s, dOO, rOO);
     if (!active) {
-        e_out[t] = 0.0;
+        if (t < n) e_out[t] = 0.0;
 #pragma unroll
         for (int c = 0; c < 18; ++c) f[c] = 0.0;
-        return;
-    }
+    } else {
     V3 F[10];
 #pragma unroll
     for (int c = 0; c < 10; ++c) F[c] = {0.0, 0.0, 0.0};
@@ -214,6 +224,8 @@ __global__ void __launch_bounds__(128) dimer_forces_kernel(const double* __restr
         f[3 * a + 2] = v.z;
     }
     e_out[t] = sw * E_poly * CAL2JOULE;
+    }
+    store_blocks<18, 128>(f_out, cta_first, n, sh);      // single barrier call site for the whole CTA
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -295,19 +307,22 @@ __global__ void __launch_bounds__(128) trimer_forces_kernel(const double* __rest
                                                             const double* __restrict__ rinv,
                                                             const double* __restrict__ poly,
                                                             double* __restrict__ e_out, double* __restrict__ f_out) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int32_t* tr = trips + 3 * (first + t);
+    __shared__ double sh[128 * 27];
+    const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t t = cta_first + threadIdx.x;
+    double* f = sh + 27 * threadIdx.x;
     V3 s[9], rab, rac, rbc;
-    double dab, dac, dbc;
-    const bool active = trimer_sites(pos, idx, tr[0], tr[1], tr[2], box, s, rab, rac, rbc, dab, dac, dbc);
-    double* f = f_out + 27 * (size_t)t;
+    double dab = 0.0, dac = 0.0, dbc = 0.0;
+    bool active = false;
+    if (t < n) {
+        const int32_t* tr = trips + 3 * (first + t);
+        active = trimer_sites(pos, idx, tr[0], tr[1], tr[2], box, s, rab, rac, rbc, dab, dac, dbc);
+    }
     if (!active) {
-        e_out[t] = 0.0;
+        if (t < n) e_out[t] = 0.0;
 #pragma unroll
         for (int c = 0; c < 27; ++c) f[c] = 0.0;
-        return;
-    }
+    } else {
     double gab, gac, gbc;
     const double sab = f_switch(dab, R3I, R3F, gab);
     const double sac = f_switch(dac, R3I, R3F, gac);
@@ -344,6 +359,8 @@ __global__ void __launch_bounds__(128) trimer_forces_kernel(const double* __rest
         f[3 * a + 2] = F[a].z;
     }
     e_out[t] = sw * E_poly * CAL2JOULE;
+    }
+    store_blocks<27, 128>(f_out, cta_first, n, sh);      // single barrier call site for the whole CTA
 }
 
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

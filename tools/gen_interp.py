@@ -65,7 +65,13 @@ def build_tree(monos, var=None):
     return node
 
 
-def serialise(name, tab, fuse=True, class_blocks=None, with_consts=True, npair=0):
+def static_combos(recs, nm, nstatic):
+    """the `nstatic` most frequent (mask id, node variable) pairs among the fused leaf-node records"""
+    freq = collections.Counter((op - OP_MASK - nm, k) for op, k, _ in recs if OP_MASK + nm <= op < OP_MASK + 2 * nm)
+    return [c for c, _ in freq.most_common(nstatic)]
+
+
+def serialise(name, tab, fuse=True, class_blocks=None, with_consts=True, npair=0, nstatic=0):
     """-> (records, masks).  records: list of (opcode, k, payload doubles); masks: list of block-index tuples.
 
     ``class_blocks`` restricts the program to the leaves whose variable lies in those blocks (the polynomial is linear in
@@ -138,6 +144,16 @@ def serialise(name, tab, fuse=True, class_blocks=None, with_consts=True, npair=0
             recs.append((OP_LEAVE + depth - 1, node.var, []))
     emit(root, 0)
     recs.append((OP_END, 0, []))
+    if nstatic:
+        # STATIC_c = LEAFNODE_m whose node variable k is fixed by the opcode: x_k and g_k are plain registers in the
+        # handler, the shared-memory read of x_k and the read-modify-write of g_k disappear
+        nm = len(masks)
+        combos = static_combos(recs, nm, nstatic)
+        cid = {c: i for i, c in enumerate(combos)}
+        recs = [(OP_MASK + 3 * nm + cid[(op - OP_MASK - nm, k)], k, pl)
+                if (OP_MASK + nm <= op < OP_MASK + 2 * nm and (op - OP_MASK - nm, k) in cid) else (op, k, pl)
+                for op, k, pl in recs]
+        serialise.combos[name] = combos
     if npair:
         # PAIR_m = two consecutive LEAFNODE_m records evaluated by one handler with interleaved, independent chains
         pairable = pair_masks(name, masks, npair)
@@ -161,6 +177,9 @@ def pair_masks(name, masks, npair, max_slots=18):
     blocks = BLOCKS[name]
     ok = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= max_slots]
     return ok[:npair]
+
+
+serialise.combos = {}
 
 
 def rec_words(n_payload):
@@ -193,7 +212,7 @@ def pack(recs, chunk_bytes):
     return np.array([w for c in chunks for w in c], dtype=np.uint64)
 
 
-def interpret(name, words, x, chunk_bytes, masks=None):
+def interpret(name, words, x, chunk_bytes, masks=None, combos=()):
     """numpy/python reference interpreter of the packed stream (used by the CPU tests)."""
     cw = chunk_bytes // 8
     blocks = BLOCKS[name]
@@ -237,8 +256,10 @@ def interpret(name, words, x, chunk_bytes, masks=None):
                     g[j] += c * a
             pc += 1 + (n if n % 2 else n + 1)
         else:                                   # fused leaf node(s): ENTER k, const; MASK_m; LEAVE k  (x2 for PAIR_m)
-            pair = op >= OP_MASK + 2 * len(masks)
-            if pair:
+            pair = OP_MASK + 2 * len(masks) <= op < OP_MASK + 3 * len(masks)
+            if op >= OP_MASK + 3 * len(masks):
+                m = masks[combos[op - OP_MASK - 3 * len(masks)][0]]
+            elif pair:
                 m = masks[pair_masks(name, masks, 1 << 30)[op - OP_MASK - 2 * len(masks)]]
             else:
                 m = masks[op - OP_MASK - len(masks)]
@@ -269,7 +290,7 @@ def hexd(v):
 
 
 def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
-               opaque=True, cmem=False, repeat=1, npair=0):
+               opaque=True, cmem=False, repeat=1, npair=0, combos=()):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
@@ -338,9 +359,14 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("mov.f64 %vc, 0d0000000000000000; mov.f64 %vd, 0d0000000000000000; mov.f64 %ac, %one;")
     w("bar.sync 0;")
     w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
-    n_ops = OP_MASK + 2 * len(masks) + (len(pair_masks(name, masks, npair)) if npair else 0)
+    n_pairs_ops = len(pair_masks(name, masks, npair)) if npair else 0
+    n_ops = OP_MASK + 3 * len(masks) + len(combos) if combos else OP_MASK + 2 * len(masks) + n_pairs_ops
     NPRE = 6                                   # payload words of the NEXT record pre-loaded by every handler
-    w("TBL: .branchtargets " + ", ".join(f"H{i}" for i in range(n_ops)) + ";")
+    targets = [f"H{i}" for i in range(n_ops)]
+    if combos:                                   # unused pair slots of the opcode table fall through to END
+        for i in range(OP_MASK + 2 * len(masks) + n_pairs_ops, OP_MASK + 3 * len(masks)):
+            targets[i] = f"H{OP_END}"
+    w("TBL: .branchtargets " + ", ".join(targets) + ";")
 
     def preload(byte_off):
         """first NPRE payload words of the record at %sp+byte_off -> %n0..%n5 (garbage past short records: unused)"""
@@ -410,7 +436,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         tail(2)
 
     # ---- MASK_m and fused LEAFNODE_m
-    def block_handler(label, m, fused):
+    def block_handler(label, m, fused, static_k=None):
         """Hand-scheduled for in-order issue (assembled with ptxas -O1, which keeps this order): loads first, then the
         value FMAs on `nacc` independent chains, the adjoint product as late as its shared-memory operand allows, and the
         chain reduction + parent update interleaved with the (mutually independent) gradient FMAs."""
@@ -420,7 +446,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         n = len(slots)
         nwords = rec_words(n)
         head(nwords)
-        if fused:
+        xk, gk = ("%xk0", "%gk") if static_k is None else (f"%x{static_k}", f"%g{static_k}")
+        if fused and static_k is None:
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
         for i in range(NPRE, n if not FAKE else 0, 2):     # the rest of this record's payload
@@ -464,15 +491,16 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                 if len(live) % 2:
                     nxt.append(live[-1])
                 live = nxt
-            rops.append(f"fma.rn.f64 %vc, %xk0, {live[0]}, %vc;")
-            rops.append(f"fma.rn.f64 %gk, %ac, {live[0]}, %gk;")
-            rops.append("st.shared.f64 [%addr], %gk;")
+            rops.append(f"fma.rn.f64 %vc, {xk}, {live[0]}, %vc;")
+            rops.append(f"fma.rn.f64 {gk}, %ac, {live[0]}, {gk};")
+            if static_k is None:
+                rops.append("st.shared.f64 [%addr], %gk;")
         # emit: value ops, adjoint product after the first few, then gradient ops with the reduction spread between
         npre_v = min(len(vops), NPRE)
         for op in vops[:npre_v]:
             w(op)
         if fused:
-            w("mul.rn.f64 %a0, %ac, %xk0;")
+            w(f"mul.rn.f64 %a0, %ac, {xk};")
         for op in vops[npre_v:]:
             w(op)
         gap = max(1, len(gops) // (len(rops) + 1)) if rops else len(gops) + 1
@@ -548,6 +576,9 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         block_handler(f"H{OP_MASK + mi}", m, False)
     for mi, m in enumerate(masks):
         block_handler(f"H{OP_MASK + len(masks) + mi}", m, True)
+    for ci, (mi, kk) in enumerate(combos):
+        assert kk in cset, "static node variable must be a register of this class"
+        block_handler(f"H{OP_MASK + 3 * len(masks) + ci}", masks[mi], True, static_k=kk)
     pairable = pair_masks(name, masks, npair) if npair else []
     for pi, mi in enumerate(pairable):
         pair_handler(f"H{OP_MASK + 2 * len(masks) + pi}", masks[mi])
@@ -576,11 +607,14 @@ CLASSES = {            # block ids per class kernel (None = one kernel with ever
 }
 
 
-def count_fp64(recs, masks, blocks):
+def count_fp64(recs, masks, blocks, combos=()):
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
-        if op >= OP_MASK + 2 * len(masks):
+        if op >= OP_MASK + 3 * len(masks):
+            n_fp += 2 * sum(len(blocks[b]) for b in masks[combos[op - OP_MASK - 3 * len(masks)][0]]) + 4
+            hist["static"] += 1
+        elif op >= OP_MASK + 2 * len(masks):
             pm = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= 18]
             n_fp += 2 * (2 * sum(len(blocks[b]) for b in masks[pm[op - OP_MASK - 2 * len(masks)]]) + 4)
             hist["pair"] += 1
@@ -602,7 +636,7 @@ def count_fp64(recs, masks, blocks):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
-             npair=0):
+             npair=0, nstatic=0):
     """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
     Returns (meta, [(words, masks) per class])."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
@@ -617,9 +651,10 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
     hist = collections.Counter()
     smem = 0
     for ci, cb in enumerate(classes):
-        recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair)
+        recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair, nstatic=nstatic)
+        combos = serialise.combos.get(name, []) if nstatic else []
         words = pack(recs, chunk)
-        f, h = count_fp64(recs, masks, blocks)
+        f, h = count_fp64(recs, masks, blocks, combos)
         n_fp += f
         hist.update(h)
         sym = f"{name}_stream{ci}"
@@ -630,10 +665,10 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
         cvars = sorted(v for b in cb for v in blocks[b])
         entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
         kl, sm = kernel_ptx(name, entry, sym, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
-                            npair=npair)
+                            npair=npair, combos=combos)
         lines += [""] + kl
         smem = max(smem, sm)
-        streams.append((words, masks))
+        streams.append((words, masks, combos))
         kernels.append({"entry": entry, "vars": len(cvars), "masks": len(masks), "stream_bytes": int(words.nbytes),
                         "fp64_instr": f})
     interpret.masks[name] = streams[0][1]
@@ -659,10 +694,13 @@ def main():
     ap.add_argument("--classes2", type=int, default=1)
     ap.add_argument("--piece", type=int, default=16, choices=[8, 16], help="stream bytes each thread stages per chunk")
     ap.add_argument("--npair", type=int, default=0, help="pair handlers for the N most frequent masks")
+    ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
+    ap.add_argument("--nstatic3", type=int, default=0)
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
         meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse,
-                           args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair)
+                           args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair,
+                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3)
         print(meta)
 
 
