@@ -41,26 +41,28 @@ def test_table_reproduces_reference_polynomial_values(name):
         assert np.abs(G - grad).max() <= 1e-12 * np.abs(grad).max()
 
 
-@pytest.mark.parametrize("name,n_classes", [("pip2b", 1), ("pip3b", 1), ("pip2b", 2), ("pip3b", 2), ("pip3b", 3)])
-def test_command_stream_matches_table(name, n_classes, tmp_path):
+@pytest.mark.parametrize("name,n_classes,opts", [
+    ("pip2b", 1, {}), ("pip3b", 1, {}), ("pip2b", 2, {}), ("pip3b", 2, {}), ("pip3b", 3, {}),
+    ("pip3b", 1, {"npair": 8}), ("pip2b", 1, {"nstatic": 32}), ("pip3b", 1, {"nstatic": 48})])
+def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
     """python interpreter of the packed streams (the same records the GPU kernels execute) vs the monomial definition;
     with several variable classes the partial values and gradients of the class streams must add up."""
-    meta, streams = gen_interp.generate(name, str(tmp_path), n_classes=n_classes)
+    meta, streams = gen_interp.generate(name, str(tmp_path), n_classes=n_classes, **opts)
     assert len(streams) == n_classes == len(meta["kernels"])
     t = dict(np.load(os.path.join(DATA, name + ".npz")))
     rng = np.random.default_rng(11)
     for _ in range(2):
         x = rng.uniform(0.05, 1.6, int(t["n_vars"]))
         E, G = 0.0, 0.0
-        for words, masks in streams:
-            e, g = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks)
+        for words, masks, combos in streams:
+            e, g = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, combos)
             E, G = E + e, G + g
         Er, Gr = extract_pip.eval_table(t, x)
         assert abs(E - Er) <= 1e-13 * max(1.0, abs(Er))
         assert np.abs(G - Gr).max() <= 1e-13 * np.abs(Gr).max()
     # stream layout invariants the kernel relies on
     cw = meta["chunk_bytes"] // 8
-    for words, _ in streams:
+    for words, _, _ in streams:
         assert len(words) % cw == 0 and not words[-cw:].any()           # trailing all-zero look-ahead chunk
     assert meta["smem_bytes"] <= 227 * 1024
 
