@@ -559,7 +559,9 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         rops = ["fma.rn.f64 %vc, %xk0, %u0, %vc;", "fma.rn.f64 %vd, %xkb, %u2, %vd;",
                 "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u2, %gkb;",
                 "st.shared.f64 [%addr], %gk;", "st.shared.f64 [%addrb], %gkb;"]
-        gops = [op for pair in zip(seq["A"][1], seq["B"][1]) for op in pair]
+        # all gradient FMAs of A (adjoint %a0 stays in the operand-reuse cache), then all of B: zipping them would
+        # alternate the adjoint operand and put two dependent updates of the same g_j back to back
+        gops = seq["A"][1] + seq["B"][1]
         gap = max(1, len(gops) // (len(rops) + 1))
         gi = 0
         for r in rops:
