@@ -304,3 +304,32 @@ def test_nocutoff_method_is_infinite_nonperiodic_cutoff():
     ctx.getPotentialEnergy()
     check_case(ctx, g)
     assert len(ctx.getTriplets()) == 364
+
+
+def test_rectangular_box_and_unwrapped_positions(checker):
+    """non-cubic box (L, L, 2L) with molecules scattered over several periodic images: same lists / energies / forces"""
+    from oracle.refbind import canonical
+    g = load_golden("water512_cell")
+    L = float(g["box"][0])
+    rng = np.random.default_rng(5)
+    pos = np.concatenate([g["pos_mol"], g["pos_mol"] + np.array([0, 0, L])])
+    pos = pos + rng.normal(0, 0.004, size=(len(pos), 1, 3))
+    box = np.array([L, L, 2 * L])
+    pos = pos + (rng.integers(-2, 3, size=(len(pos), 1, 3)) * box)        # whole molecules moved to other images
+    n = len(pos)
+    ctx = make_context(n, box, True)
+    ctx.setPositions(pos.reshape(-1, 3))
+    ctx.getPotentialEnergy()
+    f = ctx.getForces()
+    if checker.kind != "reference":
+        pytest.skip("needs the reference build (the C port list build is O(n^2))")
+    posO = pos[:, 0].copy()
+    pairs = canonical(checker.pairs(posO, box, True, 0.65))
+    trips = canonical(checker.triplets(posO, box, True, 0.45))
+    assert np.array_equal(ctx.getPairs(), pairs) and np.array_equal(ctx.getTriplets(), trips)
+    idx = np.arange(3 * n).reshape(n, 3)
+    e2, f2 = checker.eval_2b(pos.reshape(-1, 3), idx, pairs, box, True, 0.65)
+    e3, f3 = checker.eval_3b(pos.reshape(-1, 3), idx, trips, box, True, 0.45)
+    assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= E_RTOL * abs(e2)
+    assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= E_RTOL * abs(e3)
+    assert np.abs(f - (f2 + f3)).max() < F_ATOL
