@@ -290,7 +290,7 @@ def hexd(v):
 
 
 def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
-               opaque=True, cmem=False, repeat=1, npair=0, combos=()):
+               opaque=True, cmem=False, repeat=1, npair=0, combos=(), split_tail=False):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
@@ -310,7 +310,10 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     pfld = "ld.global.nc.v2.f64 {%pf0, %pf1}" if piece == 16 else "ld.global.nc.f64 %pf0"
     pfst = "{%pf0, %pf1}" if piece == 16 else "%pf0"
     pfty = "v2.f64" if piece == 16 else "f64"
-    SX, SG, SB = 0, nv * NT * 8, 2 * nv * NT * 8       # smem: x copy | g accumulators | 2 stream buffers
+    # smem: x copy | g accumulators [| second g accumulator array (split_tail)] | 2 stream buffers
+    SX, SG = 0, nv * NT * 8
+    SG2 = 2 * nv * NT * 8
+    SB = (3 if split_tail else 2) * nv * NT * 8
     out = []
     w = out.append
     w(f".visible .entry {entry}(.param .u64 p_x, .param .u64 p_out, .param .u32 p_n, .param .u32 p_ld, .param .u32 p_acc)")
@@ -354,6 +357,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w(f"ld.global.nc.f64 %x{i}, [%px]; add.u64 %px, %px, %ldb;")
     for i in range(nv):
         w(f"st.shared.f64 [%sx+{i * NT * 8}], %x{i}; st.shared.f64 [%sg+{i * NT * 8}], 0d0000000000000000;")
+        if split_tail:
+            w(f"st.shared.f64 [%sg+{i * NT * 8 + SG2 - SG}], 0d0000000000000000;")
         if i in cset:
             w(f"mov.f64 %g{i}, 0d0000000000000000;")
     w("mov.f64 %vc, 0d0000000000000000; mov.f64 %vd, 0d0000000000000000; mov.f64 %ac, %one;")
@@ -450,6 +455,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         if fused and static_k is None:
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
+            if split_tail:
+                w(f"ld.shared.f64 %gkb, [%addr+{SG2 - SG}];")
         for i in range(NPRE, n if not FAKE else 0, 2):     # the rest of this record's payload
             if i + 1 < n:
                 w(f"{LD}.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [{SPV}+{8 + 8 * i}];")
@@ -481,6 +488,12 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             for extra, base in (("%u2", "%vc"), ("%u3", "%vd")):
                 if extra in acc and extra in started:
                     rops.append(f"add.rn.f64 {base}, {base}, {extra};")
+        elif split_tail and static_k is None and len([a for a in acc if a in started]) == 2:
+            # no reduction: each value chain feeds its own parent accumulator and its own g_k accumulator array, so the
+            # record ends with independent FMA -> STS pairs instead of a DADD -> DFMA -> STS chain
+            rops += [f"fma.rn.f64 %vc, {xk}, %u0, %vc;", f"fma.rn.f64 %vd, {xk}, %u1, %vd;",
+                     "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u1, %gkb;",
+                     "st.shared.f64 [%addr], %gk;", f"st.shared.f64 [%addr+{SG2 - SG}], %gkb;"]
         else:
             live = [a for a in acc if a in started]
             while len(live) > 1:
@@ -593,6 +606,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("st.global.f64 [%po], %vc; add.u64 %po, %po, %ldb;")
     for i in range(nv):
         w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
+        if split_tail:
+            w(f"ld.shared.f64 %gkb, [%sg+{i * NT * 8 + SG2 - SG}]; add.rn.f64 %gk, %gk, %gkb;")
         if i in cset:
             w(f"add.rn.f64 %gk, %gk, %g{i};")
         w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
@@ -638,7 +653,7 @@ def count_fp64(recs, masks, blocks, combos=()):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
-             npair=0, nstatic=0):
+             npair=0, nstatic=0, split_tail=False):
     """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
     Returns (meta, [(words, masks) per class])."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
@@ -667,7 +682,7 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
         cvars = sorted(v for b in cb for v in blocks[b])
         entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
         kl, sm = kernel_ptx(name, entry, sym, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
-                            npair=npair, combos=combos)
+                            npair=npair, combos=combos, split_tail=split_tail)
         lines += [""] + kl
         smem = max(smem, sm)
         streams.append((words, masks, combos))
@@ -698,11 +713,12 @@ def main():
     ap.add_argument("--npair", type=int, default=0, help="pair handlers for the N most frequent masks")
     ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
     ap.add_argument("--nstatic3", type=int, default=0)
+    ap.add_argument("--split-tail", action="store_true", help="second g_k accumulator array: no reduction chain at record end")
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
         meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse,
                            args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair,
-                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3)
+                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail)
         print(meta)
 
 
