@@ -392,6 +392,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w("brx.idx %nop, TBL;")                 # per-handler dispatch: ptxas can hoist the jump-table read
 
     FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
+    ALIAS = int(os.environ.get("PIP_FAKE_ALIAS", "0"))          # timing experiment only: fold x/g onto N registers
 
     def coef(i):
         if FAKE:
@@ -476,6 +477,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                 started.add("%u0")
                 continue
             a = acc[i % len(acc)]
+            if ALIAS:
+                j = j % ALIAS
             if a in started:
                 vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
             else:
@@ -608,7 +611,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
         if split_tail:
             w(f"ld.shared.f64 %gkb, [%sg+{i * NT * 8 + SG2 - SG}]; add.rn.f64 %gk, %gk, %gkb;")
-        if i in cset:
+        if i in cset and (not int(os.environ.get("PIP_FAKE_ALIAS", "0")) or i < int(os.environ.get("PIP_FAKE_ALIAS", "0"))):
             w(f"add.rn.f64 %gk, %gk, %g{i};")
         w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
         w("st.global.f64 [%po], %gk; add.u64 %po, %po, %ldb;")
