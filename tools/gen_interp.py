@@ -196,7 +196,7 @@ def pack(recs, chunk_bytes):
     cur = [0]
     for op, k, payload in recs:
         need = rec_words(len(payload))
-        if len(cur) + need + 8 > cw:              # room for OP_NEXT + the 6-word look-ahead the handlers preload
+        if len(cur) + need + 18 > cw:             # room for OP_NEXT + the look-ahead words the handlers preload
             cur += [OP_NEXT, 0]
             cur += [0] * (cw - len(cur))
             chunks.append(cur)
@@ -320,7 +320,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w(f".maxntid {NT}, 1, 1")
     w(f".minnctapersm {min_blocks}")
     w("{")
-    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<64>, %vc, %vd, %ac, %w, %cst, %gk, %one, %u0, %u1, %a0, %xk0, %pf0, %pf1, %n<6>, %u2, %u3;")
+    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<64>, %vc, %vd, %ac, %w, %cst, %gk, %one, %u0, %u1, %a0, %xk0, %pf0, %pf1, %n<16>, %u2, %u3;")
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %spv, %z, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %a1, %xkb, %gkb;")
@@ -366,7 +366,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
     n_pairs_ops = len(pair_masks(name, masks, npair)) if npair else 0
     n_ops = OP_MASK + 3 * len(masks) + len(combos) if combos else OP_MASK + 2 * len(masks) + n_pairs_ops
-    NPRE = 6                                   # payload words of the NEXT record pre-loaded by every handler
+    NPRE = int(os.environ.get("PIP_NPRE", "6"))   # payload words of the NEXT record pre-loaded by every handler
     targets = [f"H{i}" for i in range(n_ops)]
     if combos:                                   # unused pair slots of the opcode table fall through to END
         for i in range(OP_MASK + 2 * len(masks) + n_pairs_ops, OP_MASK + 3 * len(masks)):
