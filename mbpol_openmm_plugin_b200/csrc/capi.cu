@@ -7,6 +7,7 @@
 // which is what ReferenceCalcMBPol{Two,Three}BodyForceKernel::execute does on the CPU
 // (platforms/reference/src/MBPolReferenceKernels.cpp:362-399, 451-483).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -199,6 +200,7 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
                                      cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(MBPOL_ECUDA, "copying particle indices failed");
     cudaMemset(ctx->d_energy.ptr, 0, 2 * sizeof(double));
+    if (const char* f = getenv("MBPOL_FORCE_TWO_PASS")) ctx->lists.force_two_pass = f[0] == '1';
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evp) cudaEventCreate(&e);
     *out = ctx;

@@ -221,6 +221,93 @@ __global__ void row_fill_kernel(const double* __restrict__ posO, int n, GridArg 
     low3[i] = sort_row(r3, n3, i);
 }
 
+// Fast path: one warp per molecule, ONE pass.  Only lower-index neighbours are kept (nothing downstream reads the upper
+// part of a row); candidates are compacted with ballot/popc into a shared-memory staging row, rank-sorted by the warp and
+// written to fixed-stride rows (ROW_CAP2 / ROW_CAP3 entries).  A row that does not fit raises `overflow` and the caller
+// falls back to the two-pass CSR path above -- same lists either way.
+constexpr int ROW_CAP2 = 64, ROW_CAP3 = 32, ROWS_WARPS = 8;
+
+__global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
+    const double* __restrict__ posO, int n, GridArg g, const int* __restrict__ cell_start,
+    const int* __restrict__ cell_members, double c2sq, double c3sq, int* __restrict__ nbr2, int* __restrict__ nbr3,
+    int* __restrict__ low2, int* __restrict__ low3, int64_t* __restrict__ ro2, int64_t* __restrict__ ro3,
+    int* __restrict__ overflow) {
+    __shared__ int s2[ROWS_WARPS][ROW_CAP2], s3[ROWS_WARPS][ROW_CAP3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * ROWS_WARPS + warp;
+    if (w >= n) return;
+    const int i = cell_members[w];
+    const unsigned lt = (1u << lane) - 1u;
+    int c[3], lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c[d] = cell_coord(posO[3 * i + d], d, g);
+        if (g.periodic) {
+            if (g.nc[d] >= 3) { lo[d] = c[d] - 1; hi[d] = c[d] + 1; }
+            else { lo[d] = 0; hi[d] = g.nc[d] - 1; }
+        } else {
+            lo[d] = max(c[d] - 1, 0);
+            hi[d] = min(c[d] + 1, g.nc[d] - 1);
+        }
+    }
+    int n2 = 0, n3 = 0;
+    for (int x = lo[0]; x <= hi[0]; ++x) {
+        const int wx = (x + g.nc[0]) % g.nc[0];
+        for (int y = lo[1]; y <= hi[1]; ++y) {
+            const int wy = (y + g.nc[1]) % g.nc[1];
+            for (int z = lo[2]; z <= hi[2]; ++z) {
+                const int wz = (z + g.nc[2]) % g.nc[2];
+                const int cell = (wx * g.nc[1] + wy) * g.nc[2] + wz;
+                const int beg = cell_start[cell], end = cell_start[cell + 1];
+                for (int k0 = beg; k0 < end; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int j = k < end ? cell_members[k] : -1;
+                    bool p2 = false, p3 = false;
+                    if (j >= 0 && j < i) {          // distance from the higher index, like the reference
+                        const double d2 = screened_d2(posO + 3 * i, posO + 3 * j, g, c2sq, c3sq);
+                        p2 = d2 <= c2sq;
+                        p3 = d2 <= c3sq;
+                    }
+                    const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
+                    if (p2) {
+                        const int pos = n2 + __popc(b2 & lt);
+                        if (pos < ROW_CAP2) s2[warp][pos] = j;
+                    }
+                    if (p3) {
+                        const int pos = n3 + __popc(b3 & lt);
+                        if (pos < ROW_CAP3) s3[warp][pos] = j;
+                    }
+                    n2 += __popc(b2);
+                    n3 += __popc(b3);
+                }
+            }
+        }
+    }
+    if (n2 > ROW_CAP2 || n3 > ROW_CAP3) {
+        if (lane == 0) atomicExch(overflow, 1);
+        return;
+    }
+    __syncwarp();
+    for (int e = lane; e < n2; e += 32) {               // rank sort: all entries are distinct
+        const int v = s2[warp][e];
+        int r = 0;
+        for (int t = 0; t < n2; ++t) r += s2[warp][t] < v;
+        nbr2[(size_t)i * ROW_CAP2 + r] = v;
+    }
+    for (int e = lane; e < n3; e += 32) {
+        const int v = s3[warp][e];
+        int r = 0;
+        for (int t = 0; t < n3; ++t) r += s3[warp][t] < v;
+        nbr3[(size_t)i * ROW_CAP3 + r] = v;
+    }
+    if (lane == 0) {
+        low2[i] = n2;
+        low3[i] = n3;
+        ro2[i] = (int64_t)i * ROW_CAP2;
+        ro3[i] = (int64_t)i * ROW_CAP3;
+    }
+}
+
 // pairs[p] = (I, J) for J in the lower part of I's row; p = pstart[I] + rank
 __global__ void emit_pairs_kernel(int n, const int64_t* __restrict__ ro, const int* __restrict__ nbr,
                                   const int* __restrict__ low, const int64_t* __restrict__ pstart,
@@ -442,32 +529,62 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     RES(ro3, n + 1, int64_t);
     RES(low2, n + 1, int);
     RES(low3, n + 1, int);
-    CK(cudaMemsetAsync(cnt2.ptr, 0, sizeof(int) * (n + 1), s));
-    CK(cudaMemsetAsync(cnt3.ptr, 0, sizeof(int) * (n + 1), s));
-    CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
-    CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
-    row_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
-                                               c2sq, c3sq, cnt2.as<int>(), cnt3.as<int>()); MBPOL_COUNT_LAUNCH(1);
-    if ((rc = exclusive_scan(cnt2.as<int>(), ro2.as<int64_t>(), n, cub_tmp, s, err))) return rc;
-    if ((rc = exclusive_scan(cnt3.as<int>(), ro3.as<int64_t>(), n, cub_tmp, s, err))) return rc;
     int64_t tot[2];
-    CK(cudaMemcpyAsync(&tot[0], ro2.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&tot[1], ro3.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    RES(nbr2, tot[0] + 1, int);
-    RES(nbr3, tot[1] + 1, int);
-    row_fill_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
-                                              c2sq, c3sq, ro2.as<int64_t>(), ro3.as<int64_t>(), nbr2.as<int>(),
-                                              nbr3.as<int>(), low2.as<int>(), low3.as<int>()); MBPOL_COUNT_LAUNCH(1);
-
-    // ---- pair lists (2B pairs, 3B hub pairs) ----------------------------------------------------------------------
+    auto two_pass_rows = [&]() -> int {                 // general CSR path: any row length
+        CK(cudaMemsetAsync(cnt2.ptr, 0, sizeof(int) * (n + 1), s));
+        CK(cudaMemsetAsync(cnt3.ptr, 0, sizeof(int) * (n + 1), s));
+        CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
+        CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
+        row_count_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(),
+                                                   cell_members.as<int>(), c2sq, c3sq, cnt2.as<int>(), cnt3.as<int>());
+        MBPOL_COUNT_LAUNCH(1);
+        int r;
+        if ((r = exclusive_scan(cnt2.as<int>(), ro2.as<int64_t>(), n, cub_tmp, s, err))) return r;
+        if ((r = exclusive_scan(cnt3.as<int>(), ro3.as<int64_t>(), n, cub_tmp, s, err))) return r;
+        CK(cudaMemcpyAsync(&tot[0], ro2.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&tot[1], ro3.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if ((r = nbr2.reserve(sizeof(int) * (size_t)(tot[0] + 1), err))) return r;
+        if ((r = nbr3.reserve(sizeof(int) * (size_t)(tot[1] + 1), err))) return r;
+        row_fill_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(),
+                                                  c2sq, c3sq, ro2.as<int64_t>(), ro3.as<int64_t>(), nbr2.as<int>(),
+                                                  nbr3.as<int>(), low2.as<int>(), low3.as<int>());
+        MBPOL_COUNT_LAUNCH(1);
+        return MBPOL_OK;
+    };
+    auto pair_offsets = [&](int* overflow_host) -> int {
+        int r;
+        if ((r = exclusive_scan(low2.as<int>(), pstart.as<int64_t>(), n, cub_tmp, s, err))) return r;
+        if ((r = exclusive_scan(low3.as<int>(), qstart.as<int64_t>(), n, cub_tmp, s, err))) return r;
+        CK(cudaMemcpyAsync(&tot[0], pstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&tot[1], qstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (overflow_host) CK(cudaMemcpyAsync(overflow_host, scratch.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return MBPOL_OK;
+    };
     RES(pstart, n + 1, int64_t);
     RES(qstart, n + 1, int64_t);
-    if ((rc = exclusive_scan(low2.as<int>(), pstart.as<int64_t>(), n, cub_tmp, s, err))) return rc;
-    if ((rc = exclusive_scan(low3.as<int>(), qstart.as<int64_t>(), n, cub_tmp, s, err))) return rc;
-    CK(cudaMemcpyAsync(&tot[0], pstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&tot[1], qstart.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    bool fast = !force_two_pass;
+    if (fast) {
+        RES(nbr2, (size_t)n * ROW_CAP2 + 1, int);
+        RES(nbr3, (size_t)n * ROW_CAP3 + 1, int);
+        RES(scratch, 8, int64_t);
+        CK(cudaMemsetAsync(scratch.ptr, 0, sizeof(int), s));
+        CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
+        CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
+        rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+            posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), c2sq, c3sq, nbr2.as<int>(),
+            nbr3.as<int>(), low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(), scratch.as<int>());
+        MBPOL_COUNT_LAUNCH(1);
+        int overflow = 0;
+        if ((rc = pair_offsets(&overflow))) return rc;
+        if (overflow) fast = false;                      // some row exceeded the fixed stride: redo with the CSR path
+    }
+    if (!fast) {
+        if ((rc = two_pass_rows())) return rc;
+        if ((rc = pair_offsets(nullptr))) return rc;
+    }
+    used_fast_rows = fast;
     n_pairs = tot[0];
     n_qpairs = tot[1];
     RES(pairs, 2 * n_pairs + 2, int32_t);

@@ -33,6 +33,8 @@ struct DeviceBuf {
 struct TupleLists {
     int n = 0;                       // molecules
     bool has2 = false, has3 = false;
+    bool force_two_pass = false;     // MBPOL_FORCE_TWO_PASS=1: skip the fixed-stride fast path (tests cover both)
+    bool used_fast_rows = false;
     int64_t n_pairs = 0, n_qpairs = 0, n_trips = 0;
     // owner partition of this rank: molecules [own_i0, own_i1), pairs [own_p0, own_p1), triplets [own_t0, own_t1)
     int own_i0 = 0, own_i1 = 0;

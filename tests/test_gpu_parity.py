@@ -333,3 +333,35 @@ def test_rectangular_box_and_unwrapped_positions(checker):
     assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= E_RTOL * abs(e2)
     assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= E_RTOL * abs(e3)
     assert np.abs(f - (f2 + f3)).max() < F_ATOL
+
+
+def test_row_builder_fast_path_and_fallbacks(checker, monkeypatch):
+    """lists.cu builds neighbour rows with a one-pass warp kernel into fixed-stride rows and falls back to the two-pass
+    CSR builder when a row overflows: both paths (and the forced fallback) must give the reference's lists"""
+    from oracle.refbind import canonical
+    g = load_golden("water256_bulk")
+    n = len(g["pos_mol"])
+    pos = g["pos_mol"].reshape(-1, 3)
+    # (1) forced two-pass on the periodic fixture
+    monkeypatch.setenv("MBPOL_FORCE_TWO_PASS", "1")
+    ctx = make_context(n, g["box"], True)
+    ctx.setPositions(pos)
+    ctx.getPotentialEnergy()
+    assert np.array_equal(ctx.getPairs(), g["pairs"].reshape(-1, 2)) and np.array_equal(ctx.getTriplets(), g["triplets"].reshape(-1, 3))
+    check_case(ctx, g)
+    monkeypatch.delenv("MBPOL_FORCE_TWO_PASS")
+    # (2) overflow: non-periodic, infinite 2B cutoff -> rows of up to 255 lower neighbours do not fit the fixed stride
+    ctx = make_context(n, None, False, 1e10, 0.45)
+    ctx.setPositions(pos)
+    ctx.getPotentialEnergy()
+    pairs = ctx.getPairs()
+    assert len(pairs) == n * (n - 1) // 2
+    posO = g["pos_mol"][:, 0].copy()
+    trips = canonical(checker.triplets(posO, None, False, 0.45))
+    assert np.array_equal(ctx.getTriplets(), trips)
+    idx = np.arange(3 * n).reshape(n, 3)
+    e2, f2 = checker.eval_2b(pos, idx, pairs, None, False)[:2]
+    e3, f3 = checker.eval_3b(pos, idx, trips, None, False)[:2]
+    assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= E_RTOL * abs(e2)
+    assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= E_RTOL * abs(e3)
+    assert np.abs(ctx.getForces() - (f2 + f3)).max() < F_ATOL
