@@ -324,7 +324,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %spv, %z, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %a1, %xkb, %gkb;")
-    w(".reg .pred %valid, %pacc; .reg .u32 %acc;")
+    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc;")
     w("ld.param.u32 %acc, [p_acc]; setp.ne.u32 %pacc, %acc, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
     w("cvta.to.global.u64 %px, %px; cvta.to.global.u64 %po, %po;")
@@ -383,12 +383,17 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w("mov.u32 %k, %nk;")
         w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}+{8 * nwords}];")
 
+    SELFBR = bool(int(os.environ.get("PIP_SELF_BRANCH", "0")))
+    cur_label = [None, None]
+
     def tail(nwords):
         preload(8 * nwords)
         if cmem:
             w(f"add.u64 %cp, %cp, {8 * nwords};")
         else:
             w(f"add.u32 %sp, %sp, {8 * nwords}; add.u32 %spv, %spv, {8 * nwords};")
+        if SELFBR and cur_label[0] is not None:
+            w(f"setp.eq.u32 %pself, %nop, {cur_label[1]}; @%pself bra.uni {cur_label[0]};")
         w("brx.idx %nop, TBL;")                 # per-handler dispatch: ptxas can hoist the jump-table read
 
     FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
@@ -447,6 +452,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         value FMAs on `nacc` independent chains, the adjoint product as late as its shared-memory operand allows, and the
         chain reduction + parent update interleaved with the (mutually independent) gradient FMAs."""
         w(f"{label}:")
+        cur_label[0], cur_label[1] = (label, int(label[1:])) if fused else (None, None)
         vars_ = [j for b in m for j in blocks[b]]
         slots = ([None] if fused else []) + vars_          # None = the node constant (first payload word)
         n = len(slots)
