@@ -386,8 +386,9 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     SELFBR = bool(int(os.environ.get("PIP_SELF_BRANCH", "0")))
     cur_label = [None, None]
 
-    def tail(nwords):
-        preload(8 * nwords)
+    def tail(nwords, preloaded=0):
+        for q in range(preloaded, NPRE, 2):
+            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * q}];")
         if cmem:
             w(f"add.u64 %cp, %cp, {8 * nwords};")
         else:
@@ -396,6 +397,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             w(f"setp.eq.u32 %pself, %nop, {cur_label[1]}; @%pself bra.uni {cur_label[0]};")
         w("brx.idx %nop, TBL;")                 # per-handler dispatch: ptxas can hoist the jump-table read
 
+    TRICKLE = int(os.environ.get("PIP_TRICKLE", "4"))     # preload word pair q of the next record right after its last use
     FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
     ALIAS = int(os.environ.get("PIP_FAKE_ALIAS", "0"))          # timing experiment only: fold x/g onto N registers
 
@@ -517,6 +519,28 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             rops.append(f"fma.rn.f64 {gk}, %ac, {live[0]}, {gk};")
             if static_k is None:
                 rops.append("st.shared.f64 [%addr], %gk;")
+        if TRICKLE and fused and static_k is None:
+            # slot pairs in payload order; once both FMAs of the two slots of a 16-byte payload piece are issued the
+            # piece's registers are dead and the same piece of the NEXT record is loaded into them
+            w(f"mul.rn.f64 %a0, %ac, {xk};")
+            done = 0
+            vi = gi = 0
+            for q in range(0, n, TRICKLE):
+                cnt = min(TRICKLE, n - q)
+                for u in range(cnt):
+                    w(vops[q + u])
+                for u in range(cnt):
+                    if slots[q + u] is not None:
+                        w(gops[gi])
+                        gi += 1
+                for p2 in range(q, q + cnt + (cnt & 1), 2):
+                    if p2 + 1 < NPRE:
+                        w(f"{LD}.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * p2}];")
+                        done = p2 + 2
+            for r in rops:
+                w(r)
+            tail(nwords, done)
+            return
         # emit: value ops, adjoint product after the first few, then gradient ops with the reduction spread between
         npre_v = min(len(vops), NPRE)
         for op in vops[:npre_v]:
