@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP2, FLOP3 = 30601, 111818
+NCU_DRAM_BYTES_PER_TRIMER = 472.0e6 / 887147     # profiles/r01_ncu_pip3b_eval_interp_details.txt
 NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -274,7 +275,11 @@ def main():
             "stage_ms": {"lists": acc["lists"] / k, "2b": acc["b2"] / k, "3b": acc["b3"] / k, "pip2b_eval": ms_pip2,
                          "pip3b_eval": ms_pip3},
             "roofline": {"bound": "fp64", "kernel": "pip3b_eval", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                         # dram__bytes_read+write of one `ncu --set full` capture of this kernel (profiles/
+                         # r01_ncu_pip3b_eval_interp_details.txt: 472 MB for 887,147 trimers) scaled to this launch
+                         "traffic": acc["t3"] * NCU_DRAM_BYTES_PER_TRIMER, "traffic_unit": "bytes per launch",
+                         "traffic_source": "ncu --set full, 532 B per trimer (algorithmic 584 B), scaled by trimers per launch",
                          "peak_source": "measured on this GPU: register-resident DFMA loop (mbpol_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": NOMINAL_FP64_TF, "frac_of_nominal": achieved / NOMINAL_FP64_TF,

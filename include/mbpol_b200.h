@@ -100,6 +100,18 @@ int  mbpol_eval(mbpol_ctx* ctx, const double* pos_nm, double* force, double* ene
  * This is the entry the Reference-platform-style adapter and the end-to-end benchmark use. */
 int  mbpol_eval_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, uint32_t flags);
 
+/* replaces CalcMBPolOneBodyForceKernel::execute (openmmapi/include/openmm/mbpolKernels.h:47-82,
+ * platforms/reference/src/MBPolReferenceKernels.cpp:101-114; MBPolReferenceOneBodyForce.cpp:70-210): the intramolecular
+ * Partridge-Schwenke surface of every molecule of the context (the MBPolOneBodyForce::addOneBody list is the context's
+ * particle_indices).  periodic = MBPolOneBodyForce::Periodic (hydrogens imaged to their own oxygen with the box of
+ * mbpol_set_box).  pos_nm / force: DEVICE pointers as in mbpol_eval (forces are ADDED; every particle must belong to
+ * one molecule only); energy: HOST pointer to 1 double (kJ/mol) or NULL.  With a partition (mbpol_set_partition) rank r
+ * evaluates molecules [n*r/world, n*(r+1)/world). */
+int  mbpol_eval_onebody(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, int32_t periodic,
+                        void* stream);
+/* same with HOST buffers (synchronous) */
+int  mbpol_eval_onebody_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, int32_t periodic);
+
 /* OpenMM CUDA force-buffer convention (platforms/cuda/src/kernels/twobodyForce.cu:442-457): int64 fixed point,
  * value * 2^32, SoA [x: padded][y: padded][z: padded].  Adds the forces of the last mbpol_eval (which must have been
  * called with force == NULL or not) into omm_force for the particles of this context. DEVICE pointer. */

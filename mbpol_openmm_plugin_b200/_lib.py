@@ -22,7 +22,7 @@ EXPORTS = (
     "mbpol_create", "mbpol_destroy", "mbpol_last_error", "mbpol_update_particles", "mbpol_set_box",
     "mbpol_set_partition", "mbpol_eval", "mbpol_eval_host", "mbpol_add_forces_fixed_point", "mbpol_get_pairs",
     "mbpol_get_triplets", "mbpol_get_stats", "mbpol_set_timing", "mbpol_pip_eval", "mbpol_eval_tuples",
-    "mbpol_measure_fp64_peak", "mbpol_pip_instruction_count",
+    "mbpol_measure_fp64_peak", "mbpol_pip_instruction_count", "mbpol_eval_onebody", "mbpol_eval_onebody_host",
 )
 
 
@@ -69,6 +69,8 @@ def load():
     L.mbpol_set_partition.argtypes = [vp, C.c_int32, C.c_int32]
     L.mbpol_eval.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32, vp]
     L.mbpol_eval_host.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32]
+    L.mbpol_eval_onebody.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_int32, vp]
+    L.mbpol_eval_onebody_host.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_int32]
     L.mbpol_add_forces_fixed_point.argtypes = [vp, vp, C.c_int32, vp]
     L.mbpol_get_pairs.argtypes = [vp, vp, C.POINTER(C.c_size_t)]
     L.mbpol_get_triplets.argtypes = [vp, vp, C.POINTER(C.c_size_t)]

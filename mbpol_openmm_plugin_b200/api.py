@@ -94,6 +94,63 @@ class MBPolThreeBodyForce(_MBPolManyBodyForce):
     """openmmapi/include/openmm/MBPolThreeBodyForce.h:57-166"""
 
 
+class MBPolOneBodyForce:
+    """MBPolOneBodyForce (openmmapi/include/openmm/MBPolOneBodyForce.h; SWIG python/mbpolplugin.i): the intramolecular
+    Partridge-Schwenke term, one {O,H1,H2} entry per molecule."""
+
+    NonPeriodic = 0
+    Periodic = 1
+
+    def __init__(self):
+        self._method = self.NonPeriodic
+        self._bodies = []
+        self._group = 0
+
+    def addOneBody(self, particleIndices):
+        p = [int(i) for i in particleIndices]
+        if len(p) != 3:
+            raise MBPolError(_lib.EINVAL, "addOneBody: three particle indices {O,H1,H2} are required")
+        self._bodies.append(p)
+        return len(self._bodies) - 1
+
+    def getNumOneBodys(self):
+        return len(self._bodies)
+
+    def getOneBodyParameters(self, index):
+        return list(self._bodies[index])
+
+    def setOneBodyParameters(self, index, particleIndices):
+        self._bodies[index] = [int(i) for i in particleIndices]
+
+    def getNonbondedMethod(self):
+        return self._method
+
+    def setNonbondedMethod(self, method):
+        if method not in (self.NonPeriodic, self.Periodic):
+            raise MBPolError(_lib.EINVAL, "MBPolOneBodyForce: Illegal value for nonbonded method")
+        self._method = method
+
+    def getForceGroup(self):
+        return self._group
+
+    def setForceGroup(self, group):
+        self._group = int(group)
+
+    def getNumParticles(self):
+        return len(self._bodies)
+
+    def updateParametersInContext(self, context):
+        for k in context.kernels:
+            if k.force is self:
+                k.copyParametersToContext(context, self)
+
+    def _indices(self):
+        return np.asarray(self._bodies, dtype=np.int32).reshape(-1, 3)
+
+
+DO_1B = 0x100      # host-side selector only: the one-body term has its own C-ABI entry (mbpol_eval_onebody)
+
+
 class _Engine:
     """One mbpol_ctx shared by the 2B and 3B kernels of a context (one list build per step serves both)."""
 
@@ -139,6 +196,19 @@ class _Engine:
         _lib.check(self.L.mbpol_eval_host(self.h, pos.ctypes.data, force.ctypes.data if force is not None else None,
                                           e, flags), self.h)
         return e[0], e[1]
+
+    def eval_onebody(self, pos, force, periodic, stream=None):
+        """one-body term; pos/force torch CUDA tensors or host numpy arrays, force accumulated into"""
+        e = C.c_double()
+        if isinstance(pos, np.ndarray):
+            _lib.check(self.L.mbpol_eval_onebody_host(self.h, pos.ctypes.data,
+                                                      force.ctypes.data if force is not None else None,
+                                                      C.byref(e), int(periodic)), self.h)
+        else:
+            _lib.check(self.L.mbpol_eval_onebody(self.h, pos.data_ptr(),
+                                                 force.data_ptr() if force is not None else None, C.byref(e),
+                                                 int(periodic), stream), self.h)
+        return e.value
 
     def _get_list(self, fn, width):
         n = C.c_size_t(0)
@@ -203,6 +273,21 @@ class B200CalcMBPolThreeBodyForceKernel(_B200Kernel):
         return "CalcMBPolThreeBodyForce"
 
 
+class B200CalcMBPolOneBodyForceKernel(_B200Kernel):
+    """CalcMBPolOneBodyForceKernel (openmmapi/include/openmm/mbpolKernels.h:47-82; Reference implementation
+    MBPolReferenceKernels.cpp:77-126)"""
+    _flag = DO_1B
+
+    @staticmethod
+    def Name():
+        return "CalcMBPolOneBodyForce"
+
+    def copyParametersToContext(self, context, force):
+        if force.getNumOneBodys() != self.force.getNumOneBodys():
+            raise MBPolError(_lib.ECHANGED, "updateParametersInContext: The number of stretch-bends has changed")
+        context._update_parameters(force)
+
+
 class MBPolContext:
     """The part of OpenMM's System+Context the 2B/3B path needs.
 
@@ -218,9 +303,14 @@ class MBPolContext:
         self.box = None if box_nm is None else [float(x) for x in box_nm]
         self._f2 = next((f for f in self.forces if isinstance(f, MBPolTwoBodyForce)), None)
         self._f3 = next((f for f in self.forces if isinstance(f, MBPolThreeBodyForce)), None)
-        if self._f2 is None and self._f3 is None:
-            raise MBPolError(_lib.EINVAL, "no MBPolTwoBodyForce / MBPolThreeBodyForce given")
-        ref = self._f2 or self._f3
+        self._f1 = next((f for f in self.forces if isinstance(f, MBPolOneBodyForce)), None)
+        if self._f2 is None and self._f3 is None and self._f1 is None:
+            raise MBPolError(_lib.EINVAL, "no MBPolOneBodyForce / MBPolTwoBodyForce / MBPolThreeBodyForce given")
+        ref = self._f2 or self._f3 or self._f1
+        if self._f1 is not None and not np.array_equal(self._f1._indices(), ref._indices()):
+            raise MBPolError(_lib.EINVAL, "the forces must list the same molecules")
+        if self._f1 is not None and self._f1.getNonbondedMethod() == MBPolOneBodyForce.Periodic and self.box is None:
+            raise MBPolError(_lib.EINVAL, "MBPolOneBodyForce.Periodic needs a periodic box")
         if self._f2 is not None and self._f3 is not None and not np.array_equal(self._f2._indices(), self._f3._indices()):
             raise MBPolError(_lib.EINVAL, "the two forces must list the same molecules")
         # MBPol*ForceImpl::initialize: cutoff <= box/2 for periodic systems (MBPolTwoBodyForceImpl.cpp:60-66)
@@ -241,7 +331,8 @@ class MBPolContext:
             self.engine.set_partition(rank, world)
         self.kernels = []
         self._flags = 0
-        for f, K in ((self._f2, B200CalcMBPolTwoBodyForceKernel), (self._f3, B200CalcMBPolThreeBodyForceKernel)):
+        for f, K in ((self._f1, B200CalcMBPolOneBodyForceKernel), (self._f2, B200CalcMBPolTwoBodyForceKernel),
+                     (self._f3, B200CalcMBPolThreeBodyForceKernel)):
             if f is not None:
                 k = K(K.Name(), self)
                 k.initialize(None, f)
@@ -261,20 +352,33 @@ class MBPolContext:
     def _execute(self, flags):
         if self._pos is None:
             raise MBPolError(_lib.EINVAL, "positions have not been set")
-        if isinstance(self._pos, np.ndarray):
+        host = isinstance(self._pos, np.ndarray)
+        stream = None
+        if host:
             if self._force_out is not None:
                 f = self._force_out
                 f[...] = 0.0
             else:
                 f = np.zeros_like(self._pos)
-            e2, e3 = self.engine.eval_host(self._pos, f, flags)
         else:
             import torch
             f = torch.zeros_like(self._pos)
-            e2, e3 = self.engine.eval_device(self._pos, f, flags, stream=torch.cuda.current_stream().cuda_stream)
+            stream = torch.cuda.current_stream().cuda_stream
+        self.energies = {}
+        total = 0.0
+        if flags & DO_1B:
+            e1 = self.engine.eval_onebody(self._pos, f, self._f1.getNonbondedMethod() == MBPolOneBodyForce.Periodic,
+                                          stream)
+            self.energies["CalcMBPolOneBodyForce"] = e1
+            total += e1
+        if flags & (_lib.DO_2B | _lib.DO_3B):
+            many = flags & (_lib.DO_2B | _lib.DO_3B)
+            e2, e3 = self.engine.eval_host(self._pos, f, many) if host else \
+                self.engine.eval_device(self._pos, f, many, stream=stream)
+            self.energies.update({"CalcMBPolTwoBodyForce": e2, "CalcMBPolThreeBodyForce": e3})
+            total += e2 + e3
         self._forces = f
-        self.energies = {"CalcMBPolTwoBodyForce": e2, "CalcMBPolThreeBodyForce": e3}
-        return e2 + e3
+        return total
 
     # -- user-facing ----------------------------------------------------------------------------------------
     def setPeriodicBoxVectors(self, a, b=None, c=None):

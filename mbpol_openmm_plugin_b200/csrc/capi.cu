@@ -31,7 +31,7 @@ struct mbpol_ctx {
     TupleLists lists;
     ContributionIndex ci2, ci3;
     DeviceBuf x2, r2, o2, e2, f2, x3, r3, o3, e3, f3;
-    DeviceBuf f_mol, e_partial, d_energy, pos_stage, force_stage;
+    DeviceBuf f_mol, e_partial, d_energy, pos_stage, force_stage, e1;
     cudaEvent_t ev[6] = {}, evp[4] = {};      // stage events; events around the two polynomial kernels
     bool f_mol_valid = false;
 };
@@ -194,7 +194,7 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
     std::string err;
     if (ctx->idx.reserve(sizeof(int32_t) * (3 * (size_t)ctx->n_mol + 4), err) ||
         ctx->f_mol.reserve(sizeof(double) * (9 * (size_t)ctx->n_mol + 9), err) ||
-        ctx->e_partial.reserve(sizeof(double) * 1024, err) || ctx->d_energy.reserve(sizeof(double) * 2, err))
+        ctx->e_partial.reserve(sizeof(double) * 1024, err) || ctx->d_energy.reserve(sizeof(double) * 4, err))
         return bail(MBPOL_ENOMEM, err);
     if (ctx->n_mol > 0 && cudaMemcpy(ctx->idx.ptr, cfg->particle_indices, sizeof(int32_t) * 3 * (size_t)ctx->n_mol,
                                      cudaMemcpyHostToDevice) != cudaSuccess)
@@ -305,6 +305,47 @@ int mbpol_eval_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double*
     if (force) CKC(cudaMemcpyAsync(ctx->force_stage.ptr, force, bytes, cudaMemcpyHostToDevice, s));
     if ((rc = mbpol_eval(ctx, ctx->pos_stage.as<double>(), force ? ctx->force_stage.as<double>() : nullptr, energy,
                          flags, (void*)s)))
+        return rc;
+    if (force) CKC(cudaMemcpyAsync(force, ctx->force_stage.ptr, bytes, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    return MBPOL_OK;
+}
+
+int mbpol_eval_onebody(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, int32_t periodic, void* stream) {
+    if (!ctx || !pos_nm) return fail(ctx, MBPOL_EINVAL, "mbpol_eval_onebody: null argument");
+    if (periodic && !(ctx->box[0] > 0 && ctx->box[1] > 0 && ctx->box[2] > 0))
+        return fail(ctx, MBPOL_EBOX, "mbpol_eval_onebody: periodic evaluation needs a box (mbpol_set_box)");
+    cudaStream_t s = (cudaStream_t)stream;
+    CKC(cudaSetDevice(ctx->device));
+    g_launches = 0;
+    const int first = (int)((int64_t)ctx->n_mol * ctx->rank / ctx->world);
+    const int n = (int)((int64_t)ctx->n_mol * (ctx->rank + 1) / ctx->world) - first;
+    int rc;
+    if ((rc = ctx->e1.reserve(sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->err))) return rc;
+    BoxArg box{{ctx->box[0], ctx->box[1], ctx->box[2]}, periodic ? 1 : 0};
+    launch_onebody(pos_nm, ctx->idx.as<int32_t>(), first, n, box, force, ctx->e1.as<double>(), s);
+    launch_energy_sum(ctx->e1.as<double>(), n, ctx->e_partial.as<double>(), ctx->d_energy.as<double>() + 2, s);
+    if (energy) {
+        CKC(cudaMemcpyAsync(energy, ctx->d_energy.as<double>() + 2, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CKC(cudaStreamSynchronize(s));
+    }
+    ctx->stats.n_launches = g_launches;
+    CKC(cudaGetLastError());
+    return MBPOL_OK;
+}
+
+int mbpol_eval_onebody_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, int32_t periodic) {
+    if (!ctx || !pos_nm) return fail(ctx, MBPOL_EINVAL, "mbpol_eval_onebody_host: null argument");
+    CKC(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * 3 * (size_t)ctx->n_particles;
+    int rc;
+    if ((rc = ctx->pos_stage.reserve(bytes + 8, ctx->err))) return rc;
+    if ((rc = ctx->force_stage.reserve(bytes + 8, ctx->err))) return rc;
+    cudaStream_t s = 0;
+    CKC(cudaMemcpyAsync(ctx->pos_stage.ptr, pos_nm, bytes, cudaMemcpyHostToDevice, s));
+    if (force) CKC(cudaMemcpyAsync(ctx->force_stage.ptr, force, bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = mbpol_eval_onebody(ctx, ctx->pos_stage.as<double>(), force ? ctx->force_stage.as<double>() : nullptr,
+                                 energy, periodic, (void*)s)))
         return rc;
     if (force) CKC(cudaMemcpyAsync(force, ctx->force_stage.ptr, bytes, cudaMemcpyDeviceToHost, s));
     CKC(cudaStreamSynchronize(s));

@@ -62,6 +62,10 @@ void launch_trimer_forces(const double* pos, const int32_t* idx, const int32_t* 
                           int64_t ld, BoxArg box, const double* x, const double* rinv, const double* poly, double* e,
                           double* f, cudaStream_t s);
 
+// ---- one-body term (onebody.cu): molecules [first, first+n), forces added in place, e_mol[n] in kJ/mol ----------------
+void launch_onebody(const double* pos, const int32_t* idx, int first, int n, BoxArg box, double* force, double* e_mol,
+                    cudaStream_t s);
+
 // ---- polynomial stage (pip_module.cu): generated PTX kernels loaded through the driver API --------------------------
 int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, cudaStream_t s, std::string* err);
 int pip_instruction_count(int order);

@@ -332,3 +332,83 @@ double port_eval_3b(const double* pos, double* forces, const int* idx, const int
     }
     return energy;
 }
+
+/* ---- one-body term ---------------------------------------------------------------------------
+ * Restates MBPolReferenceOneBodyForce::calculateOneBodyIxn (MBPolReferenceOneBodyForce.cpp:70-187) and
+ * calculateForceAndEnergy (:191-210).  The parameter tables (mbpol_interaction_constants.h:24-424) are handed in by
+ * refbind.py from mbpol_openmm_plugin_b200/data/onebody.npz. */
+static struct {
+    double c5z[245], reoh, b1, roh, alphaoh, deohA, phh1A, phh2, f5z, cm1_kcalmol;
+    int i1[245], i2[245], i3[245];
+} ps;
+
+void port_set_onebody(const double* c5z, const int* i1, const int* i2, const int* i3, const double* scalars) {
+    memcpy(ps.c5z, c5z, sizeof ps.c5z);
+    memcpy(ps.i1, i1, sizeof ps.i1);
+    memcpy(ps.i2, i2, sizeof ps.i2);
+    memcpy(ps.i3, i3, sizeof ps.i3);
+    ps.reoh = scalars[0]; ps.b1 = scalars[1]; ps.roh = scalars[2]; ps.alphaoh = scalars[3]; ps.deohA = scalars[4];
+    ps.phh1A = scalars[5]; ps.phh2 = scalars[6]; ps.f5z = scalars[7]; ps.cm1_kcalmol = scalars[8];
+}
+
+static double port_monomer(vec3 O, vec3 H1, vec3 H2, double* f /* 3x3: O,H1,H2 increments */) {
+    vec3 r1 = scl(sub(H1, O), 10.0), r2 = scl(sub(H2, O), 10.0), rh = scl(sub(H1, H2), 10.0);
+    const double d1 = sqrt(dot(r1, r1)), d2 = sqrt(dot(r2, r2)), dh = sqrt(dot(rh, rh));
+    const double costh = dot(r1, r2) / (d1 * d2);
+    const double deoh = ps.f5z * ps.deohA, phh1 = ps.f5z * ps.phh1A * exp(ps.phh2);
+    const double costhe = -.24780227221366464506;
+    const double e1 = exp(-ps.alphaoh * (d1 - ps.roh)), e2 = exp(-ps.alphaoh * (d2 - ps.roh));
+    const double Va = deoh * (e1 * (e1 - 2.0) + e2 * (e2 - 2.0));
+    const double Vb = phh1 * exp(-ps.phh2 * dh);
+    const double dVa1 = 2.0 * ps.alphaoh * deoh * e1 * (1.0 - e1) / d1;
+    const double dVa2 = 2.0 * ps.alphaoh * deoh * e2 * (1.0 - e2) / d2;
+    const double dVb = -ps.phh2 * Vb / dh;
+    const double x[3] = {(d1 - ps.reoh) / ps.reoh, (d2 - ps.reoh) / ps.reoh, costh - costhe};
+    double P[3][16];
+    for (int a = 0; a < 3; ++a) {
+        P[a][0] = 0.0;
+        P[a][1] = 1.0;
+        for (int j = 2; j < 16; ++j) P[a][j] = P[a][j - 1] * x[a];
+    }
+    const double efac = exp(-ps.b1 * ((d1 - ps.reoh) * (d1 - ps.reoh) + (d2 - ps.reoh) * (d2 - ps.reoh)));
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int j = 1; j < 245; ++j) {
+        const int I = ps.i1[j], J = ps.i2[j], K = ps.i3[j];
+        s0 += ps.c5z[j] * (P[0][I] * P[1][J] + P[0][J] * P[1][I]) * P[2][K];
+        s1 += ps.c5z[j] * ((I - 1) * P[0][I - 1] * P[1][J] + (J - 1) * P[0][J - 1] * P[1][I]) * P[2][K];
+        s2 += ps.c5z[j] * ((J - 1) * P[0][I] * P[1][J - 1] + (I - 1) * P[0][J] * P[1][I - 1]) * P[2][K];
+        s3 += ps.c5z[j] * (P[0][I] * P[1][J] + P[0][J] * P[1][I]) * (K - 1) * P[2][K - 1];
+    }
+    double e = Va + Vb + (2 * ps.c5z[0] + efac * s0);
+    e += 0.44739574026257;
+    e *= ps.cm1_kcalmol;
+    const double dr1 = (-2 * ps.b1 * efac * (d1 - ps.reoh) * s0 + efac * s1 / ps.reoh) / d1;
+    const double dr2 = (-2 * ps.b1 * efac * (d2 - ps.reoh) * s0 + efac * s2 / ps.reoh) / d2;
+    const double dct = efac * s3, unit = ps.cm1_kcalmol * 4.184 * 10;
+    for (int c = 0; c < 3; ++c) {
+        const double f1 = (dVa1 * r1.v[c] + dVb * rh.v[c] + dr1 * r1.v[c] +
+                           dct * (r2.v[c] / (d1 * d2) - costh * r1.v[c] / (d1 * d1))) * unit;
+        const double f2 = (dVa2 * r2.v[c] - dVb * rh.v[c] + dr2 * r2.v[c] +
+                           dct * (r1.v[c] / (d1 * d2) - costh * r2.v[c] / (d2 * d2))) * unit;
+        f[3 + c] = -f1;
+        f[6 + c] = -f2;
+        f[c] = f1 + f2;
+    }
+    return e * 4.184;
+}
+
+double port_eval_1b(const double* pos, double* forces, const int* idx, int n_mol, const double* box, int pbc) {
+    double energy = 0.0, f[9];
+    for (int m = 0; m < n_mol; ++m) {
+        const int* im = idx + 3 * m;
+        vec3 O = load(pos, im[0], 1.0), H1 = load(pos, im[1], 1.0), H2 = load(pos, im[2], 1.0);
+        if (pbc) {
+            image_to(box, &O, &H1);
+            image_to(box, &O, &H2);
+        }
+        energy += port_monomer(O, H1, H2, f);
+        if (forces)
+            for (int k = 0; k < 3; ++k) for (int c = 0; c < 3; ++c) forces[3 * im[k] + c] += f[3 * k + c];
+    }
+    return energy;
+}

@@ -63,6 +63,9 @@ class Ref:
         for fn in (L.ref_poly2b, L.ref_poly3b):
             fn.restype = C.c_double
             fn.argtypes = [_dp, _dp]
+        if hasattr(L, "ref_eval_1b"):
+            L.ref_eval_1b.restype = C.c_double
+            L.ref_eval_1b.argtypes = [_dp, _dp, C.c_long, _ip, C.c_int, _dp, C.c_int]
         L.ref_ncoef2b.restype = L.ref_ncoef3b.restype = C.c_int
         L.ref_coef2b.restype = L.ref_coef3b.restype = _dp
 
@@ -103,6 +106,15 @@ class Ref:
 
     def eval_3b(self, pos, idx, trip, box, pbc, cutoff=1e10):
         return self._eval(self.lib.ref_eval_3b, pos, idx, trip, box, pbc, cutoff)
+
+    def eval_1b(self, pos, idx, box, pbc):
+        """one-body term: E (kJ/mol), F (kJ/mol/nm) summed over the molecules in idx"""
+        pos = _f64(pos)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        box = _f64(box if box is not None else [0, 0, 0])
+        f = np.zeros_like(pos)
+        e = self.lib.ref_eval_1b(_d(pos), _d(f), len(pos), idx.ctypes.data_as(_ip), len(idx), _d(box), int(bool(pbc)))
+        return e, f
 
     def _each(self, fn, width, pos_mol, tuples, box, pbc):
         pos = _f64(pos_mol).reshape(-1, 3)
@@ -163,6 +175,16 @@ class Port:
             mv = np.ascontiguousarray(t["mono_vars"], dtype=np.uint8)
             self._keep += [coef, mc, mv]
             L.port_set_tables(order, int(t["n_vars"]), len(mc), _d(coef), mc.ctypes.data_as(u16p), mv.ctypes.data_as(u8p))
+        ob = np.load(os.path.join(data, "onebody.npz"))
+        sc = np.array([float(ob[k]) for k in ("reoh", "b1", "roh", "alphaoh", "deohA", "phh1A", "phh2", "f5z",
+                                              "cm1_kcalmol")])
+        tabs = [np.ascontiguousarray(ob["c5z"], dtype=np.float64)] + \
+            [np.ascontiguousarray(ob[k], dtype=np.int32) for k in ("idx1", "idx2", "idx3")]
+        L.port_set_onebody.argtypes = [_dp, _ip, _ip, _ip, _dp]
+        L.port_set_onebody.restype = None
+        L.port_set_onebody(_d(tabs[0]), *[t.ctypes.data_as(_ip) for t in tabs[1:]], _d(sc))
+        L.port_eval_1b.restype = C.c_double
+        L.port_eval_1b.argtypes = [_dp, _dp, _ip, C.c_int, _dp, C.c_int]
         L.port_poly.restype = C.c_double
         L.port_poly.argtypes = [C.c_int, _dp, _dp]
         for fn in (L.port_pairs, L.port_triplets):
@@ -212,6 +234,14 @@ class Port:
 
     def eval_3b(self, pos, idx, trip, box, pbc, cutoff=None, each=False):
         return self._eval(self.lib.port_eval_3b, 3, pos, idx, trip, box, pbc, each)
+
+    def eval_1b(self, pos, idx, box, pbc):
+        pos = _f64(pos)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        box = _f64(box if box is not None else [0, 0, 0])
+        f = np.zeros_like(pos)
+        e = self.lib.port_eval_1b(_d(pos), _d(f), idx.ctypes.data_as(_ip), len(idx), _d(box), int(bool(pbc)))
+        return e, f
 
 
 def have_port():

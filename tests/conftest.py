@@ -77,4 +77,11 @@ def make_context(n_mol, box, pbc, cut2=0.65, cut3=0.45, stride=3, which=(2, 3), 
         for row in particle_indices(n_mol, stride):
             f.addParticle(row.tolist())
         forces.append(f)
+    if 1 in which:
+        from mbpol_openmm_plugin_b200 import MBPolOneBodyForce
+        f = MBPolOneBodyForce()
+        f.setNonbondedMethod(f.Periodic if pbc else f.NonPeriodic)
+        for row in particle_indices(n_mol, stride):
+            f.addOneBody(row.tolist())
+        forces.insert(0, f)
     return MBPolContext(n_mol * stride, forces, box_nm=list(box) if pbc else None, **kw)

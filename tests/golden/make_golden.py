@@ -42,9 +42,10 @@ def full_case(pos_mol, box, pbc, cut2, cut3):
     trips = canonical(R.triplets(posO, box, pbc, cut3))
     e2, f2 = R.eval_2b(pos, idx, pairs, box, pbc, cut2)
     e3, f3 = R.eval_3b(pos, idx, trips, box, pbc, cut3)
+    e1, f1 = R.eval_1b(pos, idx, box, pbc)               # one-body term (MBPolReferenceOneBodyForce.cpp)
     return dict(pos_mol=pos_mol, box=np.array(box if box is not None else [0, 0, 0], dtype=np.float64), pbc=np.int32(pbc),
                 cut2=np.float64(cut2), cut3=np.float64(cut3), pairs=pairs, triplets=trips, e2=np.float64(e2),
-                e3=np.float64(e3), f2=f2, f3=f3)
+                e3=np.float64(e3), f2=f2, f3=f3, e1=np.float64(e1), f1=f1)
 
 
 def main():
