@@ -67,5 +67,9 @@ class CudaSliceEngine:
         import torch
         ctx = self.ctx
         f = torch.zeros_like(pos)
-        e2, e3 = ctx.engine.eval_device(pos, f, ctx._flags, stream=torch.cuda.current_stream().cuda_stream)
+        stream = torch.cuda.current_stream().cuda_stream
+        many = ctx._flags & 3                      # MBPOL_DO_2B | MBPOL_DO_3B
+        e2, e3 = ctx.engine.eval_device(pos, f, many, stream=stream) if many else (0.0, 0.0)
+        if ctx._f1 is not None:                    # one-body term of this rank's molecule slice rides along in e2's slot
+            e2 += ctx.engine.eval_onebody(pos, f, ctx._f1.getNonbondedMethod() == ctx._f1.Periodic, stream)
         return e2, e3, f

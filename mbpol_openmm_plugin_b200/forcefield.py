@@ -4,7 +4,9 @@ Mirrors what `app.ForceField("mbpol.xml").createSystem(pdb.topology, nonbondedMe
 (python/mbpol.py:81-225): the cutoff is the element's `cutoff_nm` attribute (NOT nonbondedCutoff, mbpol.py:99,131), the
 nonbonded method maps NoCutoff / CutoffNonPeriodic / CutoffPeriodic / PME onto the plugin enum (mbpol.py:118-121), and one
 `addParticle([O, H1, H2])` is issued per HOH residue (mbpol.py:138-150).  Both the reduced XML shipped here
-(data/mbpol_2b3b.xml) and the reference's full python/mbpol.xml parse: only the two force elements are read."""
+(data/mbpol_2b3b.xml) and the reference's full python/mbpol.xml parse: only these force elements are read.
+An `<MBPolOneBodyForce>` element adds the one-body term (python/mbpol.py:12-79: NoCutoff / CutoffNonPeriodic ->
+NonPeriodic, CutoffPeriodic / PME -> Periodic, one addOneBody([O, H1, H2]) per water)."""
 from __future__ import annotations
 
 import os
@@ -12,7 +14,7 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
-from .api import MBPolContext, MBPolThreeBodyForce, MBPolTwoBodyForce
+from .api import MBPolContext, MBPolOneBodyForce, MBPolThreeBodyForce, MBPolTwoBodyForce
 
 DEFAULT_XML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mbpol_2b3b.xml")
 
@@ -54,13 +56,20 @@ class ForceField:
             el = root.find(tag)
             if el is not None:
                 self.cutoffs[tag] = float(el.attrib["cutoff_nm"])
-        if not self.cutoffs:
-            raise ValueError("no MBPolTwoBodyForce / MBPolThreeBodyForce element in " + xml_path)
+        self.one_body = root.find("MBPolOneBodyForce") is not None
+        if not self.cutoffs and not self.one_body:
+            raise ValueError("no MBPolOneBodyForce / MBPolTwoBodyForce / MBPolThreeBodyForce element in " + xml_path)
 
     def createForces(self, pdb, nonbondedMethod=CutoffNonPeriodic):
         if nonbondedMethod not in _METHOD:
             raise ValueError("Illegal nonbonded method for MBPolTwoBodyForce")
         forces = []
+        if self.one_body:
+            f = MBPolOneBodyForce()
+            f.setNonbondedMethod(f.Periodic if _METHOD[nonbondedMethod] == 1 else f.NonPeriodic)
+            for ohh in pdb.water_indices():
+                f.addOneBody(ohh)
+            forces.append(f)
         for tag, cls in (("MBPolTwoBodyForce", MBPolTwoBodyForce), ("MBPolThreeBodyForce", MBPolThreeBodyForce)):
             if tag not in self.cutoffs:
                 continue

@@ -77,6 +77,28 @@ private:
 class MBPolTwoBodyForce : public MBPolManyBodyForceBase {};
 class MBPolThreeBodyForce : public MBPolManyBodyForceBase {};
 
+// openmmapi/include/openmm/MBPolOneBodyForce.h: one {O,H1,H2} entry per molecule
+class MBPolOneBodyForce {
+public:
+    enum NonbondedMethod { NonPeriodic = 0, Periodic = 1 };
+    MBPolOneBodyForce() : nonbondedMethod(NonPeriodic), forceGroup(0) {}
+    int getNumOneBodys() const { return (int)stretchBends.size(); }
+    int addOneBody(const std::vector<int>& particleIndices) {
+        stretchBends.push_back(particleIndices);
+        return (int)stretchBends.size() - 1;
+    }
+    void getOneBodyParameters(int index, std::vector<int>& particleIndices) const { particleIndices = stretchBends[index]; }
+    void setOneBodyParameters(int index, std::vector<int>& particleIndices) { stretchBends[index] = particleIndices; }
+    NonbondedMethod getNonbondedMethod() const { return nonbondedMethod; }
+    void setNonbondedMethod(NonbondedMethod m) { nonbondedMethod = m; }
+    int getForceGroup() const { return forceGroup; }
+    void setForceGroup(int g) { forceGroup = g; }
+private:
+    NonbondedMethod nonbondedMethod;
+    int forceGroup;
+    std::vector<std::vector<int> > stretchBends;
+};
+
 class B200Context;
 
 // one mbpol_ctx shared by the two kernels of a context
@@ -123,6 +145,21 @@ public:
     void copyParametersToContext(B200Context&, const MBPolThreeBodyForce& force) { copyCommon(force); }
 };
 
+// CalcMBPolOneBodyForceKernel (openmmapi/include/openmm/mbpolKernels.h:47-82; MBPolReferenceKernels.cpp:77-126)
+class B200CalcMBPolOneBodyForceKernel {
+public:
+    static std::string Name() { return "CalcMBPolOneBodyForce"; }
+    explicit B200CalcMBPolOneBodyForceKernel(B200Context& c) : context(c) {}
+    void initialize(const MBPolOneBodyForce& force);
+    void copyParametersToContext(B200Context&, const MBPolOneBodyForce& force);
+    int forceGroup = 0;
+    bool usePBC = false;
+    int numOneBodys = 0;
+private:
+    static std::vector<int32_t> gather(const MBPolOneBodyForce& force);
+    B200Context& context;
+};
+
 struct B200State {
     double potentialEnergy = 0.0;
     std::vector<OpenMM::Vec3> forces;
@@ -133,7 +170,8 @@ struct B200State {
 class B200Context {
 public:
     // numParticles = System::getNumParticles(); box vectors like System::setDefaultPeriodicBoxVectors (rectangular)
-    B200Context(int numParticles, const MBPolTwoBodyForce* f2, const MBPolThreeBodyForce* f3, const OpenMM::Vec3* boxVectors = nullptr)
+    B200Context(int numParticles, const MBPolTwoBodyForce* f2, const MBPolThreeBodyForce* f3, const OpenMM::Vec3* boxVectors = nullptr,
+                const MBPolOneBodyForce* f1 = nullptr)
         : numParticles(numParticles), engine(new B200Engine) {
         if (boxVectors) { hasBox = true; box[0] = boxVectors[0][0]; box[1] = boxVectors[1][1]; box[2] = boxVectors[2][2]; }
         engine->cfg.abi_version = MBPOL_ABI_VERSION;
@@ -144,7 +182,12 @@ public:
         // MBPol*ForceImpl::initialize: periodic cutoff check, then createKernel(Name()) + kernel.initialize(system, owner)
         if (f2) { checkCutoff(*f2); k2.reset(new B200CalcMBPolTwoBodyForceKernel(*this)); k2->forceGroup = f2->getForceGroup(); k2->initialize(*f2); }
         if (f3) { checkCutoff(*f3); k3.reset(new B200CalcMBPolThreeBodyForceKernel(*this)); k3->forceGroup = f3->getForceGroup(); k3->initialize(*f3); }
-        if (!f2 && !f3) throw OpenMM::OpenMMException("no MBPol force in the system");
+        if (f1) {
+            if (f1->getNonbondedMethod() == MBPolOneBodyForce::Periodic && !hasBox)
+                throw OpenMM::OpenMMException("MBPolOneBodyForce: Periodic needs periodic box vectors");
+            k1.reset(new B200CalcMBPolOneBodyForceKernel(*this)); k1->forceGroup = f1->getForceGroup(); k1->initialize(*f1);
+        }
+        if (!f1 && !f2 && !f3) throw OpenMM::OpenMMException("no MBPol force in the system");
         engine->cfg.particle_indices = engine->indices.data();
         int rc = mbpol_create(&engine->ctx, &engine->cfg);
         if (rc != MBPOL_OK) throw OpenMM::OpenMMException(mbpol_last_error(nullptr));
@@ -166,11 +209,16 @@ public:
         if (k3 && (groups & (1 << k3->forceGroup))) flags |= MBPOL_DO_3B;
         B200State st;
         st.forces.assign(numParticles, OpenMM::Vec3());
+        static_assert(sizeof(OpenMM::Vec3) == 3 * sizeof(double), "Vec3 must be three packed doubles");
+        if (k1 && (groups & (1 << k1->forceGroup))) {
+            double e1 = 0;
+            engine->check(mbpol_eval_onebody_host(engine->ctx, &positions[0][0], &st.forces[0][0], &e1, k1->usePBC ? 1 : 0));
+            st.potentialEnergy += e1;
+        }
         if (!flags) return st;
         double e[2] = {0, 0};
-        static_assert(sizeof(OpenMM::Vec3) == 3 * sizeof(double), "Vec3 must be three packed doubles");
         engine->check(mbpol_eval_host(engine->ctx, &positions[0][0], &st.forces[0][0], e, flags));
-        st.potentialEnergy = e[0] + e[1];
+        st.potentialEnergy += e[0] + e[1];
         return st;
     }
     B200Engine& getEngine() { return *engine; }
@@ -187,10 +235,43 @@ private:
     double box[3] = {0, 0, 0};
     std::vector<OpenMM::Vec3> positions;
     std::unique_ptr<B200Engine> engine;
+    std::unique_ptr<B200CalcMBPolOneBodyForceKernel> k1;
     std::unique_ptr<B200CalcMBPolTwoBodyForceKernel> k2;
     std::unique_ptr<B200CalcMBPolThreeBodyForceKernel> k3;
     friend class B200KernelBase;
+    friend class B200CalcMBPolOneBodyForceKernel;
 };
+
+inline std::vector<int32_t> B200CalcMBPolOneBodyForceKernel::gather(const MBPolOneBodyForce& force) {
+    std::vector<int32_t> idx;
+    for (int i = 0; i < force.getNumOneBodys(); ++i) {
+        std::vector<int> p;
+        force.getOneBodyParameters(i, p);
+        if (p.size() < 3) throw OpenMM::OpenMMException("MBPolOneBodyForce: each entry needs particle indices {O, H1, H2}");
+        idx.insert(idx.end(), p.begin(), p.begin() + 3);
+    }
+    return idx;
+}
+
+inline void B200CalcMBPolOneBodyForceKernel::initialize(const MBPolOneBodyForce& force) {
+    // ReferenceCalcMBPolOneBodyForceKernel::initialize (MBPolReferenceKernels.cpp:86-99)
+    B200Engine& e = *context.engine;
+    numOneBodys = force.getNumOneBodys();
+    std::vector<int32_t> idx = gather(force);
+    if (!e.indices.empty() && e.indices != idx) throw OpenMM::OpenMMException("MBPolForce: the forces must list the same molecules");
+    e.indices = idx;
+    e.cfg.n_molecules = numOneBodys;
+    usePBC = force.getNonbondedMethod() == MBPolOneBodyForce::Periodic;
+}
+
+inline void B200CalcMBPolOneBodyForceKernel::copyParametersToContext(B200Context&, const MBPolOneBodyForce& force) {
+    if (numOneBodys != force.getNumOneBodys())       // MBPolReferenceKernels.cpp:117-118
+        throw OpenMM::OpenMMException("updateParametersInContext: The number of stretch-bends has changed");
+    B200Engine& e = *context.engine;
+    std::vector<int32_t> idx = gather(force);
+    e.check(mbpol_update_particles(e.ctx, numOneBodys, idx.data()));
+    e.indices = idx;
+}
 
 inline void B200KernelBase::initializeCommon(const MBPolManyBodyForceBase& force, bool twoBody) {
     // ReferenceCalcMBPol*ForceKernel::initialize (platforms/reference/src/MBPolReferenceKernels.cpp:341-360, 430-449)

@@ -99,6 +99,30 @@ void testThreeBody(double boxDimension, bool addPositionOffset, int particlesPer
     delete mbpolThreeBodyForce;
 }
 
+// platforms/reference/tests/TestReferenceMBPolOneBodyForce.cpp:52-140 (testOneOneBody): same molecule, same expected
+// gradients (kcal/mol/A) and energy; the reference's tolerance is 1e-4
+void testOneBody(double boxDimension) {
+    MBPolOneBodyForce force;
+    std::vector<int> ids = {0, 1, 2};
+    force.addOneBody(ids);
+    std::vector<Vec3> positions = makePositions(1, 3, boxDimension, false, 0.0);
+    Vec3 boxv[3] = {Vec3(boxDimension, 0, 0), Vec3(0, boxDimension, 0), Vec3(0, 0, boxDimension)};
+    if (boxDimension > 0) {
+        force.setNonbondedMethod(MBPolOneBodyForce::Periodic);
+        positions[1] = positions[1] + Vec3(boxDimension, 0, 0);        // a hydrogen one box edge away from its oxygen
+    }
+    B200Context context(3, nullptr, nullptr, boxDimension > 0 ? boxv : nullptr, &force);
+    context.setPositions(positions);
+    B200State state = context.getState();
+    const double expectedGrad[3][3] = {{-27.48162433, 8.92495995, 2.80995323}, {30.78909844, -11.48714187, -0.27204770},
+                                       {-3.30747410, 2.56218193, -2.53790553}};
+    ASSERT_EQUAL_TOL(0.55975882, state.getPotentialEnergy() / CalToJoule, 1e-8);
+    for (int i = 0; i < 3; ++i) {
+        Vec3 f = state.getForces()[i] * (1.0 / (CalToJoule * 10));
+        ASSERT_EQUAL_VEC(Vec3(-expectedGrad[i][0], -expectedGrad[i][1], -expectedGrad[i][2]), f, 1e-7);
+    }
+}
+
 void testErrors() {
     MBPolTwoBodyForce force;
     force.setCutoff(0.65);
@@ -129,6 +153,8 @@ int main() {
         testThreeBody(50, false, 3, 0.0);
         testThreeBody(50, true, 3, 0.0);
         testThreeBody(50, false, 4, 25.0);      // TestCudaMBPolThreeBodyForce.cpp: M sites, positions offset by +25 nm
+        testOneBody(0);
+        testOneBody(50);
         testErrors();
     } catch (const std::exception& e) {
         std::cout << "exception: " << e.what() << std::endl;

@@ -28,7 +28,9 @@ def test_xml_and_pdb_parsing(tmp_path):
     assert len(pdb.atoms) == 56 and pdb.water_indices()[1] == [4, 5, 6]
     field = ff.ForceField()
     assert field.cutoffs == {"MBPolTwoBodyForce": 0.65, "MBPolThreeBodyForce": 0.45}          # python/mbpol.xml:31-36
-    f2, f3 = field.createForces(pdb, ff.PME)
+    f1, f2, f3 = field.createForces(pdb, ff.PME)
+    assert field.one_body and f1.getNumOneBodys() == 14 and f1.getNonbondedMethod() == f1.Periodic   # python/mbpol.py:46-49
+    assert field.createForces(pdb, ff.NoCutoff)[0].getNonbondedMethod() == f1.NonPeriodic
     assert f2.getNonbondedMethod() == f2.CutoffPeriodic and f3.getCutoff() == 0.45 and f2.getNumMolecules() == 14
     with pytest.raises(ValueError):
         field.createForces(pdb, "Ewald")
@@ -50,4 +52,10 @@ def test_context_from_pdb(tmp_path):
     assert len(ctx.getPairs()) >= 70 and np.isfinite(e)
     f = ctx.getForces().reshape(14, 4, 3)
     assert np.all(f[:, 3] == 0.0)
-    assert abs(e - (float(g["e2"]) + float(g["e3"]))) < 2.0     # kJ/mol: rounding of the PDB coordinates only
+    many = ctx.energies["CalcMBPolTwoBodyForce"] + ctx.energies["CalcMBPolThreeBodyForce"]
+    assert abs(many - (float(g["e2"]) + float(g["e3"]))) < 2.0     # kJ/mol: rounding of the PDB coordinates only
+    # the one-body surface is stiff (~1e3 kJ/mol/A^2 per O-H): compare it on the rounded coordinates themselves
+    from oracle.refbind import best
+    e1, _ = best().eval_1b(pdb.positions, np.asarray(pdb.water_indices()), None, False)
+    assert abs(ctx.energies["CalcMBPolOneBodyForce"] - e1) <= 1e-9 * abs(e1)
+    assert abs(e - (many + e1)) < 1e-9
