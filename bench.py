@@ -269,7 +269,7 @@ def main():
             "frac_of_nominal_fp64_peak": (n_pairs * FLOP2 + n_trips * FLOP3) * args.steps / (ms * 1e-3) / 1e12
                                          / (NOMINAL_FP64_TF * world),
             "e2e": {"value": e2e, "unit": "water-steps/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(pos_host.numel() * 8 * (2 if world == 1 else 1)),
+                    "h2d_bytes_per_step": int(pos_host.numel() * 8),
                     "d2h_bytes_per_step": int(f_host.numel() * 8 + 16)},
             "gpu_launches": int(acc["launches"]),
             "stage_ms": {"lists": acc["lists"] / k, "2b": acc["b2"] / k, "3b": acc["b3"] / k, "pip2b_eval": ms_pip2,

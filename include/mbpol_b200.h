@@ -42,6 +42,8 @@ extern "C" {
 #define MBPOL_DO_2B        1u     /* evaluate the MBPolTwoBodyForce term   */
 #define MBPOL_DO_3B        2u     /* evaluate the MBPolThreeBodyForce term */
 #define MBPOL_KEEP_LISTS   4u     /* reuse the tuple lists of the previous call (default: rebuild, like the reference) */
+#define MBPOL_OVERWRITE_FORCES 8u /* mbpol_eval_host only: `force` is output-only (not read, not added to): saves the
+                                     host->device copy of the force array */
 
 typedef struct mbpol_ctx mbpol_ctx;
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG, "libmbpol_b200.so")
 ABI_VERSION = 1
 OK, EINVAL, ECUDA, EBOX, ECHANGED, ENOMEM = 0, -1, -2, -3, -4, -5
 NOCUTOFF, CUTOFF_PERIODIC, CUTOFF_NONPERIODIC = 0, 1, 2
-DO_2B, DO_3B, KEEP_LISTS = 1, 2, 4
+DO_2B, DO_3B, KEEP_LISTS, OVERWRITE_FORCES = 1, 2, 4, 8
 FLOP_PER_DIMER, FLOP_PER_TRIMER = 30601, 111818
 
 # every symbol include/mbpol_b200.h declares (checked by tests/test_abi.py)

@@ -354,12 +354,15 @@ class MBPolContext:
             raise MBPolError(_lib.EINVAL, "positions have not been set")
         host = isinstance(self._pos, np.ndarray)
         stream = None
+        many = flags & (_lib.DO_2B | _lib.DO_3B)
+        overwrite = host and many and not flags & DO_1B     # the many-body call may then write f without reading it
         if host:
             if self._force_out is not None:
                 f = self._force_out
-                f[...] = 0.0
+                if not overwrite:
+                    f[...] = 0.0
             else:
-                f = np.zeros_like(self._pos)
+                f = np.empty_like(self._pos) if overwrite else np.zeros_like(self._pos)
         else:
             import torch
             f = torch.zeros_like(self._pos)
@@ -371,9 +374,8 @@ class MBPolContext:
                                           stream)
             self.energies["CalcMBPolOneBodyForce"] = e1
             total += e1
-        if flags & (_lib.DO_2B | _lib.DO_3B):
-            many = flags & (_lib.DO_2B | _lib.DO_3B)
-            e2, e3 = self.engine.eval_host(self._pos, f, many) if host else \
+        if many:
+            e2, e3 = self.engine.eval_host(self._pos, f, many | (_lib.OVERWRITE_FORCES if overwrite else 0)) if host else \
                 self.engine.eval_device(self._pos, f, many, stream=stream)
             self.energies.update({"CalcMBPolTwoBodyForce": e2, "CalcMBPolThreeBodyForce": e3})
             total += e2 + e3

@@ -302,7 +302,10 @@ int mbpol_eval_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double*
     if ((rc = ctx->force_stage.reserve(bytes + 8, ctx->err))) return rc;
     cudaStream_t s = 0;
     CKC(cudaMemcpyAsync(ctx->pos_stage.ptr, pos_nm, bytes, cudaMemcpyHostToDevice, s));
-    if (force) CKC(cudaMemcpyAsync(ctx->force_stage.ptr, force, bytes, cudaMemcpyHostToDevice, s));
+    if (force) {
+        if (flags & MBPOL_OVERWRITE_FORCES) CKC(cudaMemsetAsync(ctx->force_stage.ptr, 0, bytes, s));
+        else CKC(cudaMemcpyAsync(ctx->force_stage.ptr, force, bytes, cudaMemcpyHostToDevice, s));
+    }
     if ((rc = mbpol_eval(ctx, ctx->pos_stage.as<double>(), force ? ctx->force_stage.as<double>() : nullptr, energy,
                          flags, (void*)s)))
         return rc;

@@ -365,3 +365,25 @@ def test_row_builder_fast_path_and_fallbacks(checker, monkeypatch):
     assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= E_RTOL * abs(e2)
     assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= E_RTOL * abs(e3)
     assert np.abs(ctx.getForces() - (f2 + f3)).max() < F_ATOL
+
+
+def test_host_force_output_is_overwritten_not_accumulated():
+    """MBPolContext hands a preallocated (e.g. pinned) output array to mbpol_eval_host with MBPOL_OVERWRITE_FORCES: stale
+    contents must not leak into the result; the raw C-ABI call without the flag still ADDS (reference semantics)."""
+    import ctypes
+    from mbpol_openmm_plugin_b200 import _lib
+    g = load_golden("water14_xml")
+    n = len(g["pos_mol"])
+    ctx = make_context(n, g["box"], False)
+    out = np.full((3 * n, 3), np.nan)
+    ctx.setForceOutput(out)
+    ctx.setPositions(g["pos_mol"].reshape(-1, 3))
+    ctx.getPotentialEnergy()
+    assert ctx.getForces() is out
+    assert np.abs(out - (g["f2"] + g["f3"])).max() < F_ATOL
+    pos = np.ascontiguousarray(g["pos_mol"].reshape(-1, 3))
+    acc = np.ones((3 * n, 3))
+    e = (ctypes.c_double * 2)()
+    _lib.check(_lib.load().mbpol_eval_host(ctx.engine.h, pos.ctypes.data, acc.ctypes.data, e, _lib.DO_2B | _lib.DO_3B),
+               ctx.engine.h)
+    assert np.abs(acc - 1.0 - (g["f2"] + g["f3"])).max() < F_ATOL
