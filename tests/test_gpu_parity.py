@@ -387,3 +387,78 @@ def test_host_force_output_is_overwritten_not_accumulated():
     _lib.check(_lib.load().mbpol_eval_host(ctx.engine.h, pos.ctypes.data, acc.ctypes.data, e, _lib.DO_2B | _lib.DO_3B),
                ctx.engine.h)
     assert np.abs(acc - 1.0 - (g["f2"] + g["f3"])).max() < F_ATOL
+
+
+def test_full_size_262144_properties(checker):
+    """BASELINE config 5 (the bench workload: 262,144 waters, 4.8 M dimers, 7.1 M trimers).  The oracle cannot run the
+    whole box in test time, so: structural list invariants on the full lists, list membership AND completeness against
+    brute force for a sample of owner molecules, per-tuple energies / forces of a random tuple sample against the oracle,
+    Newton's third law and translation invariance on the full result."""
+    import torch
+    from mbpol_openmm_plugin_b200 import eval_tuples
+    from mbpol_openmm_plugin_b200.systems import particle_indices, synthetic_box
+    pos, box = synthetic_box(8)
+    n = len(pos)
+    assert n == 262144
+    ctx = make_context(n, box, True)
+    ctx.setPositions(torch.as_tensor(pos.reshape(-1, 3)).cuda())
+    e = ctx.getPotentialEnergy()
+    f = ctx.getForces().cpu().numpy()
+    pairs, trips = ctx.getPairs(), ctx.getTriplets()
+    st = ctx.engine.stats()
+    assert st["n_pairs"] == len(pairs) and st["n_triplets"] == len(trips)
+    assert 17.5 * n < len(pairs) < 19.5 * n and 23 * n < len(trips) < 28 * n
+    # canonical order, strict I > J (> K), no duplicates
+    assert pairs.min() >= 0 and pairs.max() < n and trips.min() >= 0 and trips.max() < n
+    assert np.all(pairs[:, 0] > pairs[:, 1]) and np.all(trips[:, 0] > trips[:, 1]) and np.all(trips[:, 1] > trips[:, 2])
+    assert np.all(np.diff(pairs[:, 0].astype(np.int64) * n + pairs[:, 1]) > 0)
+    key = (trips[:, 0].astype(np.int64) * n + trips[:, 1]) * n + trips[:, 2]
+    assert np.all(np.diff(key) > 0)
+    del key
+    # membership + completeness for sampled owners: the reference's minimum-image distance (periodicDifference,
+    # ReferenceThreeNeighborList.cpp:14-33) by brute force over ALL lower-index oxygens
+    posO = pos[:, 0]
+    rng = np.random.default_rng(5)
+
+    def lower_neighbours(i, cut):
+        d = posO[:i] - posO[i]
+        d -= box * np.floor(d / box + 0.5)
+        return set(np.nonzero((d * d).sum(axis=1) <= cut * cut)[0].tolist())
+
+    p_start = np.searchsorted(pairs[:, 0], np.arange(n + 1))
+    t_start = np.searchsorted(trips[:, 0], np.arange(n + 1))
+    for i in rng.choice(n, 60, replace=False).tolist() + [0, 1, n - 1]:
+        assert set(pairs[p_start[i]:p_start[i + 1], 1].tolist()) == lower_neighbours(i, 0.65)
+        near = lower_neighbours(i, 0.45)
+        want = {(j, k) for j in near for k in lower_neighbours(j, 0.45)}          # chain set, SURVEY.md App. B
+        assert {tuple(t) for t in trips[t_start[i]:t_start[i + 1], 1:].tolist()} == want
+    # per-tuple values of a random sample against the oracle
+    idx = particle_indices(n)
+    for order, tuples in ((2, pairs), (3, trips)):
+        sel = np.sort(rng.choice(len(tuples), 2000, replace=False))
+        eg, fg = eval_tuples(order, pos, tuples[sel], box)
+        if checker.kind == "reference":
+            er, fr = (checker.each_2b if order == 2 else checker.each_3b)(pos, tuples[sel], box, True)
+        else:
+            _, _, er, fr = (checker.eval_2b if order == 2 else checker.eval_3b)(pos.reshape(-1, 3), idx, tuples[sel], box,
+                                                                                 True, each=True)
+        assert np.abs(eg - er).max() <= 1e-9 * np.abs(er).max() and np.abs(fg - fr).max() < F_ATOL
+    # forces on the molecules of one small region against the oracle: every tuple that touches them
+    # (energy sum of those tuples is not separable, forces on the chosen molecules are)
+    probe = rng.choice(n, 3, replace=False)
+    for m in probe.tolist():
+        tp = pairs[(pairs[:, 0] == m) | (pairs[:, 1] == m)]
+        tt = trips[(trips[:, 0] == m) | (trips[:, 1] == m) | (trips[:, 2] == m)]
+        _, f2 = checker.eval_2b(pos.reshape(-1, 3), idx, tp, box, True)[:2]
+        _, f3 = checker.eval_3b(pos.reshape(-1, 3), idx, tt, box, True)[:2]
+        assert np.abs(f[3 * m:3 * m + 3] - (f2 + f3)[3 * m:3 * m + 3]).max() < F_ATOL
+    # Newton's third law over 786,432 atoms; invariance under whole-box translations of molecules
+    assert np.abs(f.sum(axis=0)).max() < 1e-5
+    shifted = pos.copy()
+    shifted[::7] += np.array([box[0], 0, 0])
+    shifted[::5] -= np.array([0, 2 * box[1], box[2]])
+    ctx.setPositions(torch.as_tensor(shifted.reshape(-1, 3)).cuda())
+    e_s = ctx.getPotentialEnergy()
+    assert abs(e_s - e) <= 1e-9 * abs(e)
+    assert np.array_equal(ctx.getPairs(), pairs)
+    assert np.abs(ctx.getForces().cpu().numpy() - f).max() < 2e-6
