@@ -35,7 +35,7 @@ def test_work_model_constants():
     from mbpol_openmm_plugin_b200 import _lib
     L = _lib.load()
     assert _lib.FLOP_PER_DIMER == 30601 and _lib.FLOP_PER_TRIMER == 111818
-    assert 25000 < L.mbpol_pip_instruction_count(2) < 40000
+    assert 15000 < L.mbpol_pip_instruction_count(2) < 40000
     assert 60000 < L.mbpol_pip_instruction_count(3) < 100000
     assert L.mbpol_pip_instruction_count(4) == -1
 

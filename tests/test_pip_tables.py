@@ -43,7 +43,10 @@ def test_table_reproduces_reference_polynomial_values(name):
 
 @pytest.mark.parametrize("name,n_classes,opts", [
     ("pip2b", 1, {}), ("pip3b", 1, {}), ("pip2b", 2, {}), ("pip3b", 2, {}), ("pip3b", 3, {}),
-    ("pip3b", 1, {"npair": 8}), ("pip2b", 1, {"nstatic": 32}), ("pip3b", 1, {"nstatic": 48})])
+    ("pip3b", 1, {"npair": 8}), ("pip2b", 1, {"nstatic": 32}), ("pip3b", 1, {"nstatic": 48}),
+    # symmetry phases (the shipped configuration: mbpol_openmm_plugin_b200/build.py GEN_ARGS) and their options
+    ("pip2b", 1, {"sym": 12, "sib": True, "fall": 4, "npre": 4}), ("pip3b", 1, {"sym": 32, "sib": True, "fall": 4, "npre": 4}),
+    ("pip2b", 1, {"sym": 16, "skeleton_weight": 0}), ("pip3b", 1, {"sym": 24, "skeleton_weight": 0})])
 def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
     """python interpreter of the packed streams (the same records the GPU kernels execute) vs the monomial definition;
     with several variable classes the partial values and gradients of the class streams must add up."""
@@ -55,7 +58,7 @@ def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
         x = rng.uniform(0.05, 1.6, int(t["n_vars"]))
         E, G = 0.0, 0.0
         for words, masks, combos in streams:
-            e, g = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, combos)
+            e, g = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, combos, meta.get("phases"))
             E, G = E + e, G + g
         Er, Gr = extract_pip.eval_table(t, x)
         assert abs(E - Er) <= 1e-13 * max(1.0, abs(Er))
@@ -65,6 +68,33 @@ def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
     for words, _, _ in streams:
         assert len(words) % cw == 0 and not words[-cw:].any()           # trailing all-zero look-ahead chunk
     assert meta["smem_bytes"] <= 227 * 1024
+    if opts.get("sym"):
+        # every variable belongs to exactly one orbit of every phase; phase 0 is the identity
+        nv = int(t["n_vars"])
+        assert meta["phases"][0] == [[j] for j in range(nv)]
+        for orbs in meta["phases"]:
+            assert sorted(v for o in orbs for v in o) == list(range(nv))
+        assert meta["fp64_instr"] < {"pip2b": 24000, "pip3b": 67000}[name]     # vs 30,180 / 79,182 without symmetry
+
+
+def test_shipped_generator_settings_are_the_tested_ones():
+    from mbpol_openmm_plugin_b200 import build
+    a = build.GEN_ARGS
+    assert (a["sym2"], a["sym3"], a["sib"], a["fall"], a["npre"]) == (12, 32, True, 4, 4)
+
+
+@pytest.mark.parametrize("name", ["pip2b", "pip3b"])
+def test_polynomial_is_invariant_under_the_site_swaps(name):
+    """the premise of the symmetry phases: exchanging the two hydrogens (or lone-pair sites) of one molecule permutes
+    the variables and leaves the polynomial unchanged"""
+    t = dict(np.load(os.path.join(DATA, name + ".npz")))
+    x = np.random.default_rng(7).uniform(0.1, 1.5, int(t["n_vars"]))
+    E, G = extract_pip.eval_table(t, x)
+    for pm in gen_interp.swap_perms(name):
+        pm = np.asarray(pm)
+        assert sorted(pm.tolist()) == list(range(len(pm))) and np.array_equal(pm[pm], np.arange(len(pm)))
+        Ep, Gp = extract_pip.eval_table(t, x[pm])
+        assert abs(Ep - E) <= 1e-13 * abs(E) and np.abs(Gp - G[pm]).max() <= 1e-13 * np.abs(G).max()
 
 
 def test_port_polynomial_matches_table(port):

@@ -39,6 +39,11 @@ BLOCKS = {
 OP_END, OP_ENTER, OP_LEAVE, OP_NEXT, OP_MASK = 0, 1, 4, 7, 8   # ENTER_d = 1..3, LEAVE_d = 4..6, MASK_m = 8 + m,
 # LEAFNODE_m = 8 + n_masks + m  (ENTER + MASK_m + LEAVE fused for nodes without children: 83 % of all nodes)
 MAX_DEPTH = 3
+# Header layout.  LOOKAHEAD: the low word of record r's header holds the opcode of record r + 1 (word 0 of the stream
+# holds the first opcode), so a handler knows its successor on entry and the jump-table read + address arithmetic of
+# its closing brx.idx no longer wait for the shared-memory load of the next header (ncu: 8 % of the warp stall cycles
+# were short-scoreboard stalls of exactly that chain).
+LOOKAHEAD = bool(int(os.environ.get("PIP_LOOKAHEAD", "1")))
 
 
 class Node:
@@ -182,6 +187,222 @@ def pair_masks(name, masks, npair, max_slots=18):
 serialise.combos = {}
 
 
+
+# ---- symmetry phases ------------------------------------------------------------------------------------------------
+# Each variable is a function of ONE site-site distance; a hydrogen (or lone-pair) swap inside one
+# molecule permutes the variables and leaves the polynomial invariant.  A Horner node whose leaf coefficients are
+# invariant under a set S of swaps is a linear form in the S-ORBIT SUMS of the variables:  sum_i c_i x_i =
+# sum_orbits c_O (sum_{i in O} x_i), and its gradient contribution is the same number for every member of an orbit.
+# The program is therefore run in PHASES, one per subgroup S that occurs: at the start of a phase the registers are
+# loaded with the orbit sums (slot = lowest variable of the orbit), the leaf handlers work on those slots only, and at
+# the end of the phase the register gradients are scattered to all orbit members.  ENTER / LEAVE keep using the
+# original variables (shared-memory copies), so the tree skeleton is the same in every phase.
+def _sites(name):
+    if name == "pip3b":
+        p = [("Ha1", "Ha2"), ("Hb1", "Hb2"), ("Hc1", "Hc2"), ("Oa", "Ha1"), ("Oa", "Ha2"), ("Ob", "Hb1"), ("Ob", "Hb2"),
+             ("Oc", "Hc1"), ("Oc", "Hc2")]
+        p += [(h, t) for h in ("Ha1", "Ha2") for t in ("Hb1", "Hb2", "Hc1", "Hc2")]
+        p += [(h, t) for h in ("Hb1", "Hb2") for t in ("Hc1", "Hc2")]
+        p += [("Oa", t) for t in ("Hb1", "Hb2", "Hc1", "Hc2")] + [("Ob", t) for t in ("Ha1", "Ha2", "Hc1", "Hc2")]
+        p += [("Oc", t) for t in ("Ha1", "Ha2", "Hb1", "Hb2")] + [("Oa", "Ob"), ("Oa", "Oc"), ("Ob", "Oc")]
+        swaps = [("Ha1", "Ha2"), ("Hb1", "Hb2"), ("Hc1", "Hc2")]
+    else:
+        p = [("Ha1", "Ha2"), ("Hb1", "Hb2"), ("Oa", "Ha1"), ("Oa", "Ha2"), ("Ob", "Hb1"), ("Ob", "Hb2")]
+        p += [(h, t) for h in ("Ha1", "Ha2") for t in ("Hb1", "Hb2")]
+        p += [("Oa", "Hb1"), ("Oa", "Hb2"), ("Ob", "Ha1"), ("Ob", "Ha2"), ("Oa", "Ob")]
+        p += [(x, t) for x in ("Xa1", "Xa2") for t in ("Hb1", "Hb2")] + [(x, t) for x in ("Xb1", "Xb2") for t in ("Ha1", "Ha2")]
+        p += [("Oa", "Xb1"), ("Oa", "Xb2"), ("Ob", "Xa1"), ("Ob", "Xa2")]
+        p += [(x, t) for x in ("Xa1", "Xa2") for t in ("Xb1", "Xb2")]
+        swaps = [("Ha1", "Ha2"), ("Hb1", "Hb2"), ("Xa1", "Xa2"), ("Xb1", "Xb2")]
+    return p, swaps
+
+
+def swap_perms(name):
+    """variable permutations induced by the site swaps"""
+    sites, swaps = _sites(name)
+    vid = {frozenset(p): i for i, p in enumerate(sites)}
+    perms = []
+    for a, b in swaps:
+        m = {a: b, b: a}
+        perms.append([vid[frozenset((m.get(p, p), m.get(q, q)))] for p, q in sites])
+    return perms
+
+
+def _orbits(nv, perms):
+    seen, orbs = set(), []
+    for v in range(nv):
+        if v in seen:
+            continue
+        o, todo = {v}, [v]
+        while todo:
+            u = todo.pop()
+            for pm in perms:
+                if pm[u] not in o:
+                    o.add(pm[u])
+                    todo.append(pm[u])
+        seen |= o
+        orbs.append(sorted(o))
+    return orbs
+
+
+def _popcount(a):
+    a = a.copy()
+    c = np.zeros(a.shape, dtype=np.int64)
+    while a.any():
+        c += (a & np.uint64(1)).astype(np.int64)
+        a >>= np.uint64(1)
+    return c
+
+
+def merge_library(req, K):
+    """req: {slot bitset: frequency}.  Agglomerative merge to K handler slot sets minimising sum(freq * |handler|)."""
+    sets, freq = [int(k) for k in sorted(req)], [int(req[k]) for k in sorted(req)]
+    while len(sets) > K:
+        s, f = np.array(sets, dtype=np.uint64), np.array(freq, dtype=np.int64)
+        pc, pu = _popcount(s), _popcount(s[:, None] | s[None, :])
+        d = f[:, None] * (pu - pc[:, None]) + f[None, :] * (pu - pc[None, :])
+        d[np.tril_indices(len(sets))] = 1 << 60
+        i, j = divmod(int(np.argmin(d)), len(sets))
+        sets[i] |= sets[j]
+        freq[i] += freq[j]
+        del sets[j], freq[j]
+    return sets
+
+
+def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
+    """-> (records, masks, phases).  masks: handler slot tuples; phases: list of orbit lists (phase 0 = identity).
+    Opcodes: MASK_h = OP_MASK + h, LEAFNODE_h = OP_MASK + nm + h, TRANSITION_p = OP_MASK + 2 nm + p (scatter the
+    register gradients of phase p, load the orbit sums of phase p + 1)."""
+    import itertools
+    nv = int(tab["n_vars"])
+    coef = tab["coef"]
+    monos = [(tuple(int(v) for v in row if v != PAD), int(c)) for row, c in zip(tab["mono_vars"], tab["mono_coef"])]
+    perms = swap_perms(name)
+    table = {tuple(sorted(vs)): c for vs, c in monos}
+    for pm in perms:                                    # the premise: the polynomial is invariant under every swap
+        assert all(table.get(tuple(sorted(pm[v] for v in vs))) == c for vs, c in monos)
+    subsets = [c for r in range(len(perms) + 1) for c in itertools.combinations(range(len(perms)), r)]
+    orbs = {S: _orbits(nv, [perms[i] for i in S]) for S in subsets}
+    root = build_tree(monos)
+    nodes = []
+
+    def walk(node, depth):
+        nodes.append((node, depth))
+        for k in node.kids:
+            walk(k, depth + 1)
+    walk(root, 0)
+    # every leaf-bearing node: the subgroups under which its leaf coefficients are invariant, with the slots each needs
+    valid = {}
+    for node, _ in nodes:
+        if node.leaves:
+            valid[id(node)] = [(S, {o[0]: node.leaves[o[0]] for o in orbs[S] if o[0] in node.leaves}) for S in subsets
+                               if all(len({node.leaves.get(v) for v in o}) == 1 for o in orbs[S])]
+
+    def classify(allowed):
+        return {i: min((c for c in v if c[0] in allowed), key=lambda c: (len(c[1]), -len(c[0]))) for i, v in valid.items()}
+
+    def cost(allowed):
+        """2 FMAs per slot + the tree skeleton repeated per phase (4 FP64 + two dispatches ~ 40 issue slots per node)"""
+        c = classify(allowed)
+        tot = 2 * sum(len(need) for _, need in c.values())
+
+        def sk(node):
+            ph = {c[id(node)][0]} if node.leaves else set()
+            for k in node.kids:
+                ph |= sk(k)
+            nonlocal tot
+            if node.kids:
+                tot += skeleton_weight * len(ph)
+            return ph
+        sk(root)
+        return tot
+    allowed = set(subsets)
+    while True:
+        allowed = {S for S, _ in classify(allowed).values()} | {()}
+        base = cost(allowed)
+        trial = [(cost(allowed - {S}), S) for S in sorted(allowed) if S != ()]
+        if not trial or min(trial)[0] >= base:
+            break
+        allowed.discard(min(trial)[1])
+    cls = classify(allowed)
+    used = sorted(allowed, key=lambda S: (len(S), S))
+    pidx = {S: i for i, S in enumerate(used)}
+    phases = [orbs[S] for S in used]
+    bits = lambda need: sum(1 << j for j in need)
+    req = collections.Counter(bits(need) for _, need in cls.values())
+    lib = merge_library(req, K)
+    fr = collections.Counter()
+    pick = {}
+    for b, f in req.items():
+        h = min((h for h in lib if h & b == b), key=lambda h: (bin(h).count("1"), h))
+        pick[b] = h
+        fr[h] += f
+    lib = [h for h, _ in fr.most_common()]
+    hid = {h: i for i, h in enumerate(lib)}
+    masks = [tuple(j for j in range(nv) if h >> j & 1) for h in lib]
+    nm = len(masks)
+    leafph = {}
+
+    def leaf_phases(node):
+        s = set()
+        if node.leaves:
+            s.add(pidx[cls[id(node)][0]])
+        for k in node.kids:
+            s |= leaf_phases(k)
+        leafph[id(node)] = s
+        return s
+    leaf_phases(root)
+    recs = []
+
+    def payload(node):
+        need = cls[id(node)][1]
+        return [coef[need[j]] if j in need else 0.0 for j in masks[hid[pick[bits(need)]]]]
+
+    def emit(node, depth, p):
+        assert depth <= MAX_DEPTH
+        own = bool(node.leaves) and pidx[cls[id(node)][0]] == p
+        kids = [k for k in node.kids if p in leafph[id(k)]]
+        const = coef[node.const] if (node.const is not None and p == min(leafph[id(node)])) else 0.0
+        h = hid[pick[bits(cls[id(node)][1])]] if own else -1
+
+        def order(k):
+            childless = not any(p in leafph[id(q)] for q in k.kids)
+            return (0, hid[pick[bits(cls[id(k)][1])]]) if childless else (1, 0)
+        kids.sort(key=order)
+        if depth > 0 and not kids:
+            assert own
+            recs.append((OP_MASK + nm + h, node.var, [const] + payload(node)))
+            return
+        if depth > 0:
+            recs.append((OP_ENTER + depth - 1, node.var, [const]))
+        else:
+            assert node.const is None
+        if own:
+            recs.append((OP_MASK + h, 0, payload(node)))
+        for k in kids:
+            emit(k, depth + 1, p)
+        if depth > 0:
+            recs.append((OP_LEAVE + depth - 1, node.var, []))
+    for p in range(len(phases)):
+        if p in leafph[id(root)]:
+            emit(root, 0, p)
+        recs.append((OP_MASK + 2 * nm + p, 0, []))
+    recs.append((OP_END, 0, []))
+    if sib:
+        # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record, one dispatch
+        base, out, i = OP_MASK + 2 * nm + len(phases), [], 0
+        while i < len(recs):
+            op, k, pl = recs[i]
+            if OP_LEAVE <= op < OP_NEXT and i + 1 < len(recs) and recs[i + 1][0] == op - OP_LEAVE + OP_ENTER:
+                out.append((base + op - OP_LEAVE, k | (recs[i + 1][1] << 8), recs[i + 1][2]))
+                i += 2
+            else:
+                out.append(recs[i])
+                i += 1
+        recs = out
+    return recs, masks, phases
+
+
 def rec_words(n_payload):
     return 1 + (n_payload if n_payload % 2 else n_payload + 1)
 
@@ -190,17 +411,21 @@ def pack(recs, chunk_bytes):
     """u64 words, organised in chunks of ``chunk_bytes`` that the kernel stages through shared memory one at a time.
     Inside a chunk, word 0 is padding so that every record header sits at byte offset 8 (mod 16) and every payload is
     16-byte aligned (payloads are padded to an odd number of words).  No record straddles a chunk: the last record of a
-    chunk is OP_NEXT.  One all-zero chunk is appended so that the kernel's look-ahead load never leaves the array."""
+    chunk is OP_NEXT.  One all-zero chunk is appended so that the kernel's look-ahead load never leaves the array.
+    With LOOKAHEAD the opcode stored in a header is the NEXT record's (see above)."""
     cw = chunk_bytes // 8
     chunks = []
     cur = [0]
+    hdrs = []                                     # (chunk index, word index, op) of every header in execution order
     for op, k, payload in recs:
         need = rec_words(len(payload))
         if len(cur) + need + 18 > cw:             # room for OP_NEXT + the look-ahead words the handlers preload
+            hdrs.append((len(chunks), len(cur), OP_NEXT))
             cur += [OP_NEXT, 0]
             cur += [0] * (cw - len(cur))
             chunks.append(cur)
             cur = [0]
+        hdrs.append((len(chunks), len(cur), op))
         cur.append(op | (k << 32))
         p = list(payload)
         if len(p) % 2 == 0:
@@ -209,25 +434,34 @@ def pack(recs, chunk_bytes):
     cur += [0] * (cw - len(cur))
     chunks.append(cur)
     chunks.append([0] * cw)
+    if LOOKAHEAD:
+        chunks[0][0] = hdrs[0][2]
+        for (c, i, _), (_, _, nxt) in zip(hdrs, hdrs[1:] + [(0, 0, OP_END)]):
+            chunks[c][i] = (chunks[c][i] & ~0xFFFFFFFF) | nxt
     return np.array([w for c in chunks for w in c], dtype=np.uint64)
 
 
-def interpret(name, words, x, chunk_bytes, masks=None, combos=()):
-    """numpy/python reference interpreter of the packed stream (used by the CPU tests)."""
+def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
+    """numpy/python reference interpreter of the packed stream (used by the CPU tests).  With ``phases`` (symmetry
+    mode) the handlers work on register slots xr / gr that hold orbit sums, ENTER / LEAVE on the original variables."""
     cw = chunk_bytes // 8
-    blocks = BLOCKS[name]
-    recs_masks = None
-    nv = sum(len(b) for b in blocks)
+    nv = sum(len(b) for b in BLOCKS[name])
+    blocks = [[j] for j in range(nv)] if phases else BLOCKS[name]
     x = np.asarray(x, dtype=np.float64)
-    g = np.zeros(nv)
+    g = np.zeros(nv)                       # the shared-memory accumulators (all of dE/dx at the end)
+    xr, gr = (x.copy(), np.zeros(nv)) if phases else (x, g)
     f = words.view(np.float64)
     masks = interpret.masks[name] if masks is None else masks
+    nm = len(masks)
     pc = 1
     v, a = 0.0, 1.0
     stack = []
+    nxt = int(words[0]) & 0xFFFFFFFF
     while True:
         hdr = int(words[pc])
         op, k = hdr & 0xFFFFFFFF, hdr >> 32
+        if LOOKAHEAD:
+            op, nxt = nxt, op
         if op == OP_END:
             return v, g
         if op == OP_NEXT:
@@ -243,7 +477,7 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=()):
             v += xk * w
             g[k] += a * w
             pc += 2
-        elif op < OP_MASK + len(masks):
+        elif op < OP_MASK + nm:
             m = masks[op - OP_MASK]
             q = pc + 1
             n = 0
@@ -252,17 +486,38 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=()):
                     c = f[q]
                     q += 1
                     n += 1
-                    v += c * x[j]
-                    g[j] += c * a
+                    v += c * xr[j]
+                    gr[j] += c * a
             pc += 1 + (n if n % 2 else n + 1)
+        elif phases and op >= OP_MASK + 2 * nm + len(phases):       # SIBLING_d: LEAVE k_old + ENTER k_new, c0
+            w = v
+            v, a, xk = stack.pop()
+            v += xk * w
+            g[k & 0xFF] += a * w
+            stack.append((v, a, x[k >> 8]))
+            a = a * x[k >> 8]
+            v = f[pc + 1]
+            pc += 2
+        elif phases and op >= OP_MASK + 2 * nm:  # transition: scatter the gradients of phase p, load phase p + 1
+            p = op - OP_MASK - 2 * nm
+            for o in phases[p]:
+                for i in o:
+                    g[i] += gr[o[0]]
+            if p + 1 < len(phases):
+                for o in phases[p + 1]:
+                    xr[o[0]] = x[o[0]]
+                    for i in o[1:]:
+                        xr[o[0]] += x[i]
+                    gr[o[0]] = 0.0
+            pc += 2
         else:                                   # fused leaf node(s): ENTER k, const; MASK_m; LEAVE k  (x2 for PAIR_m)
-            pair = OP_MASK + 2 * len(masks) <= op < OP_MASK + 3 * len(masks)
-            if op >= OP_MASK + 3 * len(masks):
-                m = masks[combos[op - OP_MASK - 3 * len(masks)][0]]
+            pair = OP_MASK + 2 * nm <= op < OP_MASK + 3 * nm
+            if op >= OP_MASK + 3 * nm:
+                m = masks[combos[op - OP_MASK - 3 * nm][0]]
             elif pair:
-                m = masks[pair_masks(name, masks, 1 << 30)[op - OP_MASK - 2 * len(masks)]]
+                m = masks[pair_masks(name, masks, 1 << 30)[op - OP_MASK - 2 * nm]]
             else:
-                m = masks[op - OP_MASK - len(masks)]
+                m = masks[op - OP_MASK - nm]
             q = pc + 1
             n = 0
             for kk in ((k & 0xFF, k >> 8) if pair else (k,)):
@@ -275,8 +530,8 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=()):
                         c = f[q]
                         q += 1
                         n += 1
-                        u += c * x[j]
-                        g[j] += c * a2
+                        u += c * xr[j]
+                        gr[j] += c * a2
                 v += x[kk] * u
                 g[kk] += a * u
             pc += 1 + (n if n % 2 else n + 1)
@@ -290,7 +545,8 @@ def hexd(v):
 
 
 def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
-               opaque=True, cmem=False, repeat=1, npair=0, combos=(), split_tail=False):
+               opaque=True, cmem=False, repeat=1, npair=0, combos=(), split_tail=False, phases=None, sib=False,
+               fall=(), npre=6):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
@@ -300,7 +556,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     starts, stores them when chunk c ends (OP_NEXT) and one bar.sync flips the buffers -- the global-load latency is
     never exposed, the handlers read coefficients with broadcast ld.shared (every lane the same address).
     Returns (lines, dynamic shared bytes)."""
-    blocks = BLOCKS[name]
+    blocks = [[j] for j in range(nv)] if phases else BLOCKS[name]      # symmetry mode: a mask is a tuple of slots
     NT = block
     CH = NT * piece                    # chunk bytes = one piece per thread
     # EXPERIMENT (cmem=True): the whole stream sits in the constant bank (<= 64 KB) and is read with uniform ld.const;
@@ -324,7 +580,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %spv, %z, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %a1, %xkb, %gkb;")
-    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc;")
+    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc; .reg .f64 %xkn; .reg .u32 %addrn;")
     w("ld.param.u32 %acc, [p_acc]; setp.ne.u32 %pacc, %acc, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
     w("cvta.to.global.u64 %px, %px; cvta.to.global.u64 %po, %po;")
@@ -366,25 +622,42 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
     n_pairs_ops = len(pair_masks(name, masks, npair)) if npair else 0
     n_ops = OP_MASK + 3 * len(masks) + len(combos) if combos else OP_MASK + 2 * len(masks) + n_pairs_ops
-    NPRE = int(os.environ.get("PIP_NPRE", "6"))   # payload words of the NEXT record pre-loaded by every handler
+    if phases:
+        assert not combos and not npair
+        n_ops = OP_MASK + 2 * len(masks) + len(phases) + (MAX_DEPTH if sib else 0)
+    NPRE = int(os.environ.get("PIP_NPRE", npre))  # payload words of the NEXT record pre-loaded by every handler
     targets = [f"H{i}" for i in range(n_ops)]
     if combos:                                   # unused pair slots of the opcode table fall through to END
         for i in range(OP_MASK + 2 * len(masks) + n_pairs_ops, OP_MASK + 3 * len(masks)):
             targets[i] = f"H{OP_END}"
     w("TBL: .branchtargets " + ", ".join(targets) + ";")
 
+    XKPRE = bool(int(os.environ.get("PIP_XKPRE", "0")))   # every handler loads x_k of the NEXT record before dispatching
+
+    def next_xk():
+        if XKPRE:
+            w(f"mad.lo.u32 %addrn, %nk, {NT * 8}, %sx; ld.shared.f64 %xkn, [%addrn];")
+
     def preload(byte_off):
         """first NPRE payload words of the record at %sp+byte_off -> %n0..%n5 (garbage past short records: unused)"""
         for q in range(0, NPRE, 2):
             w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{byte_off + 8 + 8 * q}];")
 
+    DISP = "%op" if LOOKAHEAD else "%nop"
+
     def head(nwords):
         """current k <- header fetched by the previous handler; fetch the next header"""
         w("mov.u32 %k, %nk;")
+        if LOOKAHEAD:
+            w("mov.u32 %op, %nop;")
+        if XKPRE:
+            w("mov.f64 %xk0, %xkn;")
         w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}+{8 * nwords}];")
+        next_xk()
 
     SELFBR = bool(int(os.environ.get("PIP_SELF_BRANCH", "0")))
     cur_label = [None, None]
+    fall_state = [None]
 
     def tail(nwords, preloaded=0):
         for q in range(preloaded, NPRE, 2):
@@ -394,8 +667,12 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         else:
             w(f"add.u32 %sp, %sp, {8 * nwords}; add.u32 %spv, %spv, {8 * nwords};")
         if SELFBR and cur_label[0] is not None:
-            w(f"setp.eq.u32 %pself, %nop, {cur_label[1]}; @%pself bra.uni {cur_label[0]};")
-        w("brx.idx %nop, TBL;")                 # per-handler dispatch: ptxas can hoist the jump-table read
+            w(f"setp.eq.u32 %pself, {DISP}, {cur_label[1]}; @%pself bra.uni {cur_label[0]};")
+        if fall_state[0] is not None:
+            # a second copy of this handler follows: when the next record has the same opcode no branch is taken
+            w(f"setp.ne.u32 %pself, {DISP}, {fall_state[0]}; @%pself brx.idx {DISP}, TBL;")
+            return
+        w(f"brx.idx {DISP}, TBL;")              # per-handler dispatch: ptxas can hoist the jump-table read
 
     TRICKLE = int(os.environ.get("PIP_TRICKLE", "4"))     # preload word pair q of the next record right after its last use
     FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
@@ -410,9 +687,13 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w(f".reg .u64 %cp; .reg .u32 %rep; .reg .pred %prep; mov.u32 %rep, {repeat};")
         w("RESTART:")
         w(f"mov.u64 %cp, {stream}; add.u64 %cp, %cp, 8;")
+    if LOOKAHEAD:
+        assert not opaque and not cmem
+        w("ld.shared.u32 %op, [%bufcur];")         # word 0 of the stream: the first opcode
     w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}];")
+    next_xk()
     preload(0)
-    w("brx.idx %nop, TBL;")
+    w(f"brx.idx {DISP}, TBL;")
     # ---- END
     w(f"H{OP_END}:")
     if cmem:
@@ -420,19 +701,25 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("bra.uni FINISH;")
     # ---- NEXT: publish chunk c+1 (held in registers since chunk c began), flip buffers, start fetching chunk c+2
     w(f"H{OP_NEXT}:")
+    if LOOKAHEAD:
+        w("mov.u32 %op, %nop;")
     w(f"add.u32 %addr, %bufoth, %mine; st.shared.{pfty} [%addr], {pfst};")
     w("bar.sync 0;")
     w("mov.u32 %addr, %bufcur; mov.u32 %bufcur, %bufoth; mov.u32 %bufoth, %addr;")
     w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
     w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
+    next_xk()
     preload(0)
-    w("brx.idx %nop, TBL;")
+    w(f"brx.idx {DISP}, TBL;")
     # ---- ENTER_d  (payload: const in %n0)
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_ENTER + d - 1}:")
         head(2)
-        w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk{d}, [%addr];")
+        if XKPRE:
+            w(f"mov.f64 %xk{d}, %xk0;")
+        else:
+            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk{d}, [%addr];")
         w(f"mov.f64 %vs{d}, %vc; mov.f64 %vt{d}, %vd; mov.f64 %as{d}, %ac;")
         w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
         w(f"mul.rn.f64 %ac, %ac, %xk{d};")
@@ -454,7 +741,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         value FMAs on `nacc` independent chains, the adjoint product as late as its shared-memory operand allows, and the
         chain reduction + parent update interleaved with the (mutually independent) gradient FMAs."""
         w(f"{label}:")
-        cur_label[0], cur_label[1] = (label, int(label[1:])) if fused else (None, None)
+        cur_label[0], cur_label[1] = (label, int(label[1:])) if (fused and label[1:].isdigit()) else (None, None)
         vars_ = [j for b in m for j in blocks[b]]
         slots = ([None] if fused else []) + vars_          # None = the node constant (first payload word)
         n = len(slots)
@@ -462,7 +749,8 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         head(nwords)
         xk, gk = ("%xk0", "%gk") if static_k is None else (f"%x{static_k}", f"%g{static_k}")
         if fused and static_k is None:
-            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
+            if not XKPRE:
+                w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
             if split_tail:
                 w(f"ld.shared.f64 %gkb, [%addr+{SG2 - SG}];")
@@ -623,13 +911,48 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     for mi, m in enumerate(masks):
         block_handler(f"H{OP_MASK + mi}", m, False)
     for mi, m in enumerate(masks):
-        block_handler(f"H{OP_MASK + len(masks) + mi}", m, True)
+        op = OP_MASK + len(masks) + mi
+        if op in fall:
+            fall_state[0] = op
+            block_handler(f"H{op}", m, True)
+            fall_state[0] = None
+            block_handler(f"H{op}B", m, True)
+        else:
+            block_handler(f"H{op}", m, True)
     for ci, (mi, kk) in enumerate(combos):
         assert kk in cset, "static node variable must be a register of this class"
         block_handler(f"H{OP_MASK + 3 * len(masks) + ci}", masks[mi], True, static_k=kk)
     pairable = pair_masks(name, masks, npair) if npair else []
     for pi, mi in enumerate(pairable):
         pair_handler(f"H{OP_MASK + 2 * len(masks) + pi}", masks[mi])
+    # ---- TRANSITION_p (symmetry mode): scatter the register gradients of phase p to every member of their orbit
+    # (shared-memory accumulators), then load the orbit sums of phase p + 1 and clear the register gradients
+    for p, orbs in enumerate(phases or []):
+        w(f"H{OP_MASK + 2 * len(masks) + p}:")
+        cur_label[0] = cur_label[1] = None
+        head(2)
+        for o in orbs:
+            for i in o:
+                w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}]; add.rn.f64 %gk, %gk, %g{o[0]}; st.shared.f64 [%sg+{i * NT * 8}], %gk;")
+        if p + 1 < len(phases):
+            for o in phases[p + 1]:
+                w(f"ld.shared.f64 %x{o[0]}, [%sx+{o[0] * NT * 8}]; mov.f64 %g{o[0]}, 0d0000000000000000;")
+                for i in o[1:]:
+                    w(f"ld.shared.f64 %w, [%sx+{i * NT * 8}]; add.rn.f64 %x{o[0]}, %x{o[0]}, %w;")
+        tail(2)
+    # ---- SIBLING_d (symmetry mode): LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_old | k_new << 8)
+    for d in range(1, MAX_DEPTH + 1) if (phases and sib) else []:
+        w(f"H{OP_MASK + 2 * len(masks) + len(phases) + d - 1}:")
+        head(2)
+        w("and.b32 %ka, %k, 255; shr.u32 %kb, %k, 8;")
+        w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
+        w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
+        w("add.rn.f64 %w, %vc, %vd;")
+        w(f"fma.rn.f64 %vs{d}, %xk{d}, %w, %vs{d};")          # the parent's value, still saved
+        w(f"fma.rn.f64 %gk, %as{d}, %w, %gk; st.shared.f64 [%addr], %gk;")
+        w(f"mov.f64 %xk{d}, %xkb; mul.rn.f64 %ac, %as{d}, %xkb;")
+        w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
+        tail(2)
     # ---- epilogue
     w("FINISH:")
     w("@!%valid bra DONE;")
@@ -641,7 +964,9 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
         if split_tail:
             w(f"ld.shared.f64 %gkb, [%sg+{i * NT * 8 + SG2 - SG}]; add.rn.f64 %gk, %gk, %gkb;")
-        if i in cset and (not int(os.environ.get("PIP_FAKE_ALIAS", "0")) or i < int(os.environ.get("PIP_FAKE_ALIAS", "0"))):
+        if phases:
+            pass                                  # the last TRANSITION has already scattered the register gradients
+        elif i in cset and (not int(os.environ.get("PIP_FAKE_ALIAS", "0")) or i < int(os.environ.get("PIP_FAKE_ALIAS", "0"))):
             w(f"add.rn.f64 %gk, %gk, %g{i};")
         w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
         w("st.global.f64 [%po], %gk; add.u64 %po, %po, %ldb;")
@@ -657,11 +982,20 @@ CLASSES = {            # block ids per class kernel (None = one kernel with ever
 }
 
 
-def count_fp64(recs, masks, blocks, combos=()):
+def count_fp64(recs, masks, blocks, combos=(), phases=None):
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
-        if op >= OP_MASK + 3 * len(masks):
+        if phases and op >= OP_MASK + 2 * len(masks) + len(phases):
+            n_fp += 4
+            hist["sibling"] += 1
+        elif phases and op >= OP_MASK + 2 * len(masks):
+            p = op - OP_MASK - 2 * len(masks)
+            n_fp += sum(len(o) for o in phases[p])
+            if p + 1 < len(phases):
+                n_fp += sum(len(o) - 1 for o in phases[p + 1])
+            hist["transition"] += 1
+        elif op >= OP_MASK + 3 * len(masks):
             n_fp += 2 * sum(len(blocks[b]) for b in masks[combos[op - OP_MASK - 3 * len(masks)][0]]) + 4
             hist["static"] += 1
         elif op >= OP_MASK + 2 * len(masks):
@@ -686,7 +1020,8 @@ def count_fp64(recs, masks, blocks, combos=()):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
-             npair=0, nstatic=0, split_tail=False):
+             npair=0, nstatic=0, split_tail=False, sym=0, skeleton_weight=40, sib=False,
+             fall=0, npre=6):
     """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
     Returns (meta, [(words, masks) per class])."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
@@ -700,22 +1035,34 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
     n_fp = 0
     hist = collections.Counter()
     smem = 0
+    phases, fall_ops = None, ()
     for ci, cb in enumerate(classes):
-        recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair, nstatic=nstatic)
-        combos = serialise.combos.get(name, []) if nstatic else []
-        words = pack(recs, chunk)
-        f, h = count_fp64(recs, masks, blocks, combos)
+        if sym:                                  # symmetry phases: `sym` = size of the handler library
+            assert len(classes) == 1 and not npair and not nstatic
+            recs, masks, phases = serialise_sym(name, tab, sym, skeleton_weight, sib)
+            combos = []
+            runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
+            lo, hi = OP_MASK + len(masks), OP_MASK + 2 * len(masks)
+            fall_ops = tuple(sorted(op for op, c in runs.items() if fall and c >= fall and lo <= op < hi))
+            words = pack(recs, chunk)
+            f, h = count_fp64(recs, masks, [[j] for j in range(nv)], (), phases)
+        else:
+            recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair, nstatic=nstatic)
+            combos = serialise.combos.get(name, []) if nstatic else []
+            words = pack(recs, chunk)
+            f, h = count_fp64(recs, masks, blocks, combos)
         n_fp += f
         hist.update(h)
-        sym = f"{name}_stream{ci}"
-        lines.append(f".global .align 16 .b64 {sym}[{len(words)}] = {{")
+        symbol = f"{name}_stream{ci}"
+        lines.append(f".global .align 16 .b64 {symbol}[{len(words)}] = {{")
         for i in range(0, len(words), 8):
             lines.append(", ".join("0x%016X" % int(v) for v in words[i:i + 8]) + ("," if i + 8 < len(words) else ""))
         lines.append("};")
         cvars = sorted(v for b in cb for v in blocks[b])
         entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
-        kl, sm = kernel_ptx(name, entry, sym, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
-                            npair=npair, combos=combos, split_tail=split_tail)
+        kl, sm = kernel_ptx(name, entry, symbol, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
+                            npair=npair, combos=combos, split_tail=split_tail, phases=phases, sib=sib,
+                            fall=fall_ops if sym else (), npre=npre)
         lines += [""] + kl
         smem = max(smem, sm)
         streams.append((words, masks, combos))
@@ -726,7 +1073,9 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
     with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
     meta = {"name": name, "block": block, "smem_bytes": smem, "fp64_instr": n_fp, "chunk_bytes": chunk,
-            "records": dict(hist), "kernels": kernels, "kind": "interp"}
+            "records": dict(hist), "kernels": kernels, "kind": "interp-sym" if sym else "interp",
+            "phases": phases, "handlers": [len(m) for m in streams[0][1]] if sym else None, "sib": bool(sib),
+            "lookahead": LOOKAHEAD}
     with open(os.path.join(out_dir, f"{name}_meta.json"), "w") as fh:
         json.dump(meta, fh)
     return meta, streams
@@ -747,11 +1096,20 @@ def main():
     ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
     ap.add_argument("--nstatic3", type=int, default=0)
     ap.add_argument("--split-tail", action="store_true", help="second g_k accumulator array: no reduction chain at record end")
+    ap.add_argument("--sym2", type=int, default=0, help="2B: symmetry phases with a library of N leaf handlers (0 = off)")
+    ap.add_argument("--sym3", type=int, default=0)
+    ap.add_argument("--skeleton-weight", type=int, default=40)
+    ap.add_argument("--npre", type=int, default=6, help="payload words of the next record every handler pre-loads")
+    ap.add_argument("--sib", action="store_true", help="symmetry mode: fuse LEAVE_d + ENTER_d into SIBLING_d records")
+    ap.add_argument("--fall", type=int, default=0, help="symmetry mode: duplicate leaf handlers that follow themselves "
+                    "at least N times (no taken branch between two equal records)")
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
         meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse,
                            args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair,
-                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail)
+                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail,
+                           sym=args.sym2 if name == "pip2b" else args.sym3, skeleton_weight=args.skeleton_weight,
+                           sib=args.sib, fall=args.fall, npre=args.npre)
         print(meta)
 
 
