@@ -88,7 +88,12 @@ int  mbpol_set_box(mbpol_ctx* ctx, const double box_nm[3]);
 
 /* multi-GPU owner-molecule partition: this context evaluates only the tuples whose owner (highest molecule index I)
  * falls in slice `rank` of `world` slices balanced by 30,601*dimers + 111,818*trimers per owner.
- * world = 1 (default) evaluates everything.  Forces / energies returned are then partial sums to be all-reduced. */
+ * world = 1 (default) evaluates everything.  Forces / energies returned are then partial sums to be all-reduced.
+ * The first evaluation after this call builds the full lists and fixes the rank's owner range; later evaluations
+ * rebuild, every step, only the neighbour rows that range needs (its owners + their 0.45 nm halo), and
+ * mbpol_get_pairs / mbpol_get_triplets then return the rank's own tuples.  Every MBPOL_REPARTITION_EVERY (env,
+ * default 50; 0 = always build everything) evaluations the full lists and a fresh balance are computed again.  All
+ * ranks must therefore evaluate in lockstep on the same positions (the broadcast of SURVEY.md 8e does that). */
 int  mbpol_set_partition(mbpol_ctx* ctx, int32_t rank, int32_t world);
 
 /* replaces CalcMBPol{Two,Three}BodyForceKernel::execute (MBPolReferenceKernels.cpp:362-399, 451-483).

@@ -22,6 +22,12 @@ struct mbpol_ctx {
     int method2 = MBPOL_CUTOFF_NONPERIODIC, method3 = MBPOL_CUTOFF_NONPERIODIC;
     double box[3] = {0, 0, 0};
     int rank = 0, world = 1;
+    // multi-GPU: owner range of this rank from the last FULL list build.  While it is valid, list builds are SLICED:
+    // only this rank's owners and their halo get neighbour rows (TupleLists::build).  Every rank refreshes it at the
+    // same evaluation count, from the same positions, so the ranges always tile [0, n_mol).
+    bool slice_valid = false, slice_want2 = false, slice_want3 = false, slice_periodic = false;
+    int slice_lo = 0, slice_hi = 0, slice_age = 0, repartition_every = 50;
+    int64_t full_pairs = 0, full_trips = 0;
     bool lists_valid = false;
     bool timing = false;
     std::string err;
@@ -124,10 +130,25 @@ int eval_pass(mbpol_ctx* ctx, const double* pos, bool want2, bool want3, bool pe
                        ctx->lists.has3 == want3;
     if (!reuse) {
         ctx->lists_valid = false;
+        const bool slice = ctx->world > 1 && ctx->slice_valid && ctx->slice_want2 == want2 && ctx->slice_want3 == want3 &&
+                           ctx->slice_periodic == periodic && ctx->slice_age < ctx->repartition_every;
         if ((rc = ctx->lists.build(pos, ctx->idx.as<int32_t>(), ctx->n_mol, ctx->box, periodic, c2, c3, want2, want3, s,
-                                   ctx->err)))
+                                   ctx->err, slice ? ctx->slice_lo : 0, slice ? ctx->slice_hi : -1)))
             return rc;
-        if ((rc = ctx->lists.partition(ctx->rank, ctx->world, s, ctx->err))) return rc;
+        if (ctx->lists.sliced) {
+            ++ctx->slice_age;
+        } else {
+            if ((rc = ctx->lists.partition(ctx->rank, ctx->world, s, ctx->err))) return rc;
+            ctx->slice_valid = ctx->world > 1 && ctx->repartition_every > 0;
+            ctx->slice_lo = ctx->lists.own_i0;
+            ctx->slice_hi = ctx->lists.own_i1;
+            ctx->slice_want2 = want2;
+            ctx->slice_want3 = want3;
+            ctx->slice_periodic = periodic;
+            ctx->slice_age = 0;
+            ctx->full_pairs = ctx->lists.n_pairs;
+            ctx->full_trips = ctx->lists.n_trips;
+        }
         ctx->lists_valid = true;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[1], s);
@@ -142,11 +163,11 @@ int eval_pass(mbpol_ctx* ctx, const double* pos, bool want2, bool want3, bool pe
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[3], s);
     if (want2) {
-        ctx->stats.n_pairs = ctx->lists.n_pairs;
+        ctx->stats.n_pairs = ctx->lists.sliced ? ctx->full_pairs : ctx->lists.n_pairs;
         ctx->stats.n_pairs_owned = ctx->lists.own_p1 - ctx->lists.own_p0;
     }
     if (want3) {
-        ctx->stats.n_triplets = ctx->lists.n_trips;
+        ctx->stats.n_triplets = ctx->lists.sliced ? ctx->full_trips : ctx->lists.n_trips;
         ctx->stats.n_triplets_owned = ctx->lists.own_t1 - ctx->lists.own_t0;
     }
     return MBPOL_OK;
@@ -201,6 +222,7 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
         return bail(MBPOL_ECUDA, "copying particle indices failed");
     cudaMemset(ctx->d_energy.ptr, 0, 2 * sizeof(double));
     if (const char* f = getenv("MBPOL_FORCE_TWO_PASS")) ctx->lists.force_two_pass = f[0] == '1';
+    if (const char* f = getenv("MBPOL_REPARTITION_EVERY")) ctx->repartition_every = atoi(f);   // 0: never slice
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evp) cudaEventCreate(&e);
     *out = ctx;
@@ -229,6 +251,7 @@ int mbpol_update_particles(mbpol_ctx* ctx, int32_t n_molecules, const int32_t* p
     CKC(cudaSetDevice(ctx->device));
     CKC(cudaMemcpy(ctx->idx.ptr, particle_indices, sizeof(int32_t) * 3 * (size_t)n_molecules, cudaMemcpyHostToDevice));
     ctx->lists_valid = false;
+    ctx->slice_valid = false;
     return MBPOL_OK;
 }
 
@@ -247,6 +270,7 @@ int mbpol_set_partition(mbpol_ctx* ctx, int32_t rank, int32_t world) {
     ctx->rank = rank;
     ctx->world = world;
     ctx->lists_valid = false;
+    ctx->slice_valid = false;
     return MBPOL_OK;
 }
 

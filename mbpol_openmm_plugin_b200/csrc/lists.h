@@ -35,6 +35,7 @@ struct TupleLists {
     bool has2 = false, has3 = false;
     bool force_two_pass = false;     // MBPOL_FORCE_TWO_PASS=1: skip the fixed-stride fast path (tests cover both)
     bool used_fast_rows = false;
+    bool sliced = false;             // the last build covered only this rank's owners [own_i0, own_i1) + their halo
     int64_t n_pairs = 0, n_qpairs = 0, n_trips = 0;
     // owner partition of this rank: molecules [own_i0, own_i1), pairs [own_p0, own_p1), triplets [own_t0, own_t1)
     int own_i0 = 0, own_i1 = 0;
@@ -43,10 +44,11 @@ struct TupleLists {
     DeviceBuf posO, scratch, cub_tmp;
     DeviceBuf cell_of, cell_count, cell_start64, cell_start, cell_cursor, cell_members;
     DeviceBuf cnt2, cnt3, ro2, ro3, low2, low3, nbr2, nbr3;
-    DeviceBuf pstart, qstart, pairs, qpairs, tcnt, tstart, trips, weight;
+    DeviceBuf pstart, qstart, pairs, qpairs, tcnt, tstart, trips, weight, halo, own3;
 
     int build(const double* pos, const int32_t* idx, int n_mol, const double box[3], bool periodic, double cut2,
-              double cut3, bool want2, bool want3, cudaStream_t s, std::string& err);
+              double cut3, bool want2, bool want3, cudaStream_t s, std::string& err, int slice_lo = 0,
+              int slice_hi = -1);
     int partition(int rank, int world, cudaStream_t s, std::string& err);
 };
 

@@ -223,6 +223,68 @@ def test_owner_partition_sums_to_full():
     assert max(flops) / (sum(flops) / world) < 1.02                  # balanced by the 2B+3B work model
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("pbc", [True, False])
+def test_sliced_list_build_matches_full(pbc):
+    """From the second evaluation on, a partitioned context builds neighbour rows only for its owner slice and the
+    0.45 nm halo below it (TupleLists::build, sliced).  On moved positions the slices' lists must concatenate, in rank
+    order, to exactly the full canonical lists, and energies / forces must add up to the full result."""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    rng = np.random.default_rng(77)
+    moved = pos + rng.normal(0.0, 0.01, (n, 1, 3))                   # rigid displacement of every molecule
+    p0 = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    p1 = torch.as_tensor(moved.reshape(-1, 3)).cuda()
+    full = make_context(n, box, pbc)
+    full.setPositions(p1)
+    e_full, f_full = full.getPotentialEnergy(), full.getForces()
+    pairs_full, trips_full = full.getPairs(), full.getTriplets()
+    world = 3
+    e_sum, f_sum, pairs, trips = 0.0, torch.zeros_like(f_full), [], []
+    for r in range(world):
+        ctx = make_context(n, box, pbc, rank=r, world=world)
+        ctx.setPositions(p0)
+        ctx.getPotentialEnergy()                                      # full build: fixes this rank's owner range
+        ctx.setPositions(p1)
+        e_sum += ctx.getPotentialEnergy()                             # sliced build on the moved positions
+        f_sum += ctx.getForces()
+        st = ctx.engine.stats()
+        pr, tr = ctx.getPairs(), ctx.getTriplets()
+        assert (len(pr), len(tr)) == (st["n_pairs_owned"], st["n_triplets_owned"])
+        assert len(pr) < 0.5 * len(pairs_full) and len(tr) < 0.5 * len(trips_full)      # really only the slice
+        pairs.append(pr)
+        trips.append(tr)
+    assert np.array_equal(np.concatenate(pairs), pairs_full)
+    assert np.array_equal(np.concatenate(trips), trips_full)
+    assert abs(e_sum - e_full) <= 1e-11 * abs(e_full)
+    assert (f_sum - f_full).abs().max().item() < 1e-8
+
+
+@pytest.mark.gpu
+def test_sliced_list_build_refresh_and_opt_out(monkeypatch):
+    """MBPOL_REPARTITION_EVERY=k: a full build (new balanced owner ranges) every k sliced ones; 0 disables slicing"""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    p = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    full = make_context(n, box, True)
+    full.setPositions(p)
+    full.getPotentialEnergy()
+    n_full = len(full.getTriplets())
+    for every, expect_sliced in (("2", [False, True, True, False, True]), ("0", [False] * 4)):
+        monkeypatch.setenv("MBPOL_REPARTITION_EVERY", every)
+        ctx = make_context(n, box, True, rank=1, world=2)
+        seen = []
+        for _ in expect_sliced:
+            ctx.setPositions(p)
+            ctx.getPotentialEnergy()
+            seen.append(len(ctx.getTriplets()) < n_full)
+        assert seen == expect_sliced
+
+
 def test_error_behaviour():
     from mbpol_openmm_plugin_b200 import MBPolError, _lib
     g = load_golden("water256_bulk")
