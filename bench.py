@@ -34,7 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP2, FLOP3 = 30601, 111818
-NCU_DRAM_BYTES_PER_TRIMER = 472.0e6 / 887147     # profiles/r01_ncu_pip3b_eval_interp_details.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of one pip3b_eval launch inside this benchmark (7,103,084 trimers):
+# profiles/r01_ncu_pip3b_eval_sym_details.txt
+NCU_DRAM_BYTES_PER_TRIMER = (2.055654e9 + 2.059180e9) / 7103084
 NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -179,6 +181,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
+        # "NCCL version ..." on stdout) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peak_tf, _ = measure_fp64_peak()
 
@@ -277,9 +282,9 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "pip3b_eval", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                          # dram__bytes_read+write of one `ncu --set full` capture of this kernel (profiles/
-                         # r01_ncu_pip3b_eval_interp_details.txt: 472 MB for 887,147 trimers) scaled to this launch
+                         # r01_ncu_pip3b_eval_sym_details.txt: 4.11 GB for 7,103,084 trimers) scaled to this launch
                          "traffic": acc["t3"] * NCU_DRAM_BYTES_PER_TRIMER, "traffic_unit": "bytes per launch",
-                         "traffic_source": "ncu --set full, 532 B per trimer (algorithmic 584 B), scaled by trimers per launch",
+                         "traffic_source": "ncu --set full, 579 B per trimer (algorithmic 584 B), scaled by trimers per launch",
                          "peak_source": "measured on this GPU: register-resident DFMA loop (mbpol_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": NOMINAL_FP64_TF, "frac_of_nominal": achieved / NOMINAL_FP64_TF,

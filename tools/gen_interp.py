@@ -389,12 +389,12 @@ def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
         recs.append((OP_MASK + 2 * nm + p, 0, []))
     recs.append((OP_END, 0, []))
     if sib:
-        # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record, one dispatch
+        # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record, one dispatch (k = k_new | k_old << 8)
         base, out, i = OP_MASK + 2 * nm + len(phases), [], 0
         while i < len(recs):
             op, k, pl = recs[i]
             if OP_LEAVE <= op < OP_NEXT and i + 1 < len(recs) and recs[i + 1][0] == op - OP_LEAVE + OP_ENTER:
-                out.append((base + op - OP_LEAVE, k | (recs[i + 1][1] << 8), recs[i + 1][2]))
+                out.append((base + op - OP_LEAVE, recs[i + 1][1] | (k << 8), recs[i + 1][2]))
                 i += 2
             else:
                 out.append(recs[i])
@@ -493,9 +493,9 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
             w = v
             v, a, xk = stack.pop()
             v += xk * w
-            g[k & 0xFF] += a * w
-            stack.append((v, a, x[k >> 8]))
-            a = a * x[k >> 8]
+            g[k >> 8] += a * w
+            stack.append((v, a, x[k & 0xFF]))
+            a = a * x[k & 0xFF]
             v = f[pc + 1]
             pc += 2
         elif phases and op >= OP_MASK + 2 * nm:  # transition: scatter the gradients of phase p, load phase p + 1
@@ -636,7 +636,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
 
     def next_xk():
         if XKPRE:
-            w(f"mad.lo.u32 %addrn, %nk, {NT * 8}, %sx; ld.shared.f64 %xkn, [%addrn];")
+            w(f"and.b32 %addrn, %nk, 255; mad.lo.u32 %addrn, %addrn, {NT * 8}, %sx; ld.shared.f64 %xkn, [%addrn];")
 
     def preload(byte_off):
         """first NPRE payload words of the record at %sp+byte_off -> %n0..%n5 (garbage past short records: unused)"""
@@ -940,13 +940,16 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                 for i in o[1:]:
                     w(f"ld.shared.f64 %w, [%sx+{i * NT * 8}]; add.rn.f64 %x{o[0]}, %x{o[0]}, %w;")
         tail(2)
-    # ---- SIBLING_d (symmetry mode): LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_old | k_new << 8)
+    # ---- SIBLING_d (symmetry mode): LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_new | k_old << 8)
     for d in range(1, MAX_DEPTH + 1) if (phases and sib) else []:
         w(f"H{OP_MASK + 2 * len(masks) + len(phases) + d - 1}:")
         head(2)
-        w("and.b32 %ka, %k, 255; shr.u32 %kb, %k, 8;")
+        w("shr.u32 %ka, %k, 8; and.b32 %kb, %k, 255;")
         w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
-        w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
+        if XKPRE:
+            w("mov.f64 %xkb, %xk0;")
+        else:
+            w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
         w("add.rn.f64 %w, %vc, %vd;")
         w(f"fma.rn.f64 %vs{d}, %xk{d}, %w, %vs{d};")          # the parent's value, still saved
         w(f"fma.rn.f64 %gk, %as{d}, %w, %gk; st.shared.f64 [%addr], %gk;")
