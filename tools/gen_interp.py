@@ -594,12 +594,26 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("shl.b32 %sx, %r2, 3; add.u32 %sx, %sx, %r3;")             # &xs[0][tid]
     w(f"add.u32 %sg, %sx, {SG};")                                  # &gs[0][tid]
     w(f"add.u32 %bufcur, %r3, {SB}; add.u32 %bufoth, %bufcur, {CH};")
-    w(f"mul.lo.u32 %mine, %r2, {piece};")                           # this thread's piece of a chunk
-    # stream chunk 0 -> buffer 0, chunk 1 -> registers
+    ASYNC = piece > 16            # chunks > 4 KB: cp.async straight into the idle buffer (no staging registers)
+    assert piece % 16 == 0 or not ASYNC
+
+    def async_fetch(buf):
+        """this thread's 16-byte pieces of the chunk at %gs -> shared buffer `buf` (asynchronously)"""
+        w(f"add.u32 %addr, {buf}, %mine;")
+        for q in range(piece // 16):
+            w(f"cp.async.ca.shared.global [%addr+{q * NT * 16}], [%gs+{q * NT * 16}], 16;")
+    w(f"mul.lo.u32 %mine, %r2, {16 if ASYNC else piece};")           # this thread's piece of a chunk
+    # stream chunk 0 -> buffer 0, chunk 1 -> registers (ASYNC: -> buffer 1, in flight)
     w(f"mov.u64 %gs, {stream}; cvta.to.global.u64 %gs, %gs; cvt.u64.u32 %off, %mine; add.u64 %gs, %gs, %off;")
-    w(f"{pfld}, [%gs];")
-    w(f"add.u32 %addr, %bufcur, %mine; st.shared.{pfty} [%addr], {pfst};")
-    w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
+    if ASYNC:
+        async_fetch("%bufcur")
+        w("cp.async.wait_all;")
+        w(f"add.u64 %gs, %gs, {CH};")
+        async_fetch("%bufoth")
+    else:
+        w(f"{pfld}, [%gs];")
+        w(f"add.u32 %addr, %bufcur, %mine; st.shared.{pfty} [%addr], {pfst};")
+        w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
     w("mov.f64 %one, 0d3FF0000000000000;")
     if opaque:
         # word 0 of the stream is padding (zero).  Reading one of its halves at a thread-dependent address gives a zero
@@ -703,10 +717,17 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w(f"H{OP_NEXT}:")
     if LOOKAHEAD:
         w("mov.u32 %op, %nop;")
-    w(f"add.u32 %addr, %bufoth, %mine; st.shared.{pfty} [%addr], {pfst};")
+    if ASYNC:
+        w("cp.async.wait_all;")
+    else:
+        w(f"add.u32 %addr, %bufoth, %mine; st.shared.{pfty} [%addr], {pfst};")
     w("bar.sync 0;")
     w("mov.u32 %addr, %bufcur; mov.u32 %bufcur, %bufoth; mov.u32 %bufoth, %addr;")
-    w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
+    if ASYNC:                                   # everyone has left the old buffer: refill it with chunk c + 2
+        w(f"add.u64 %gs, %gs, {CH};")
+        async_fetch("%bufoth")
+    else:
+        w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
     w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
     next_xk()
@@ -1094,7 +1115,8 @@ def main():
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--classes3", type=int, default=1, help="variable classes (kernels) for the 3B polynomial")
     ap.add_argument("--classes2", type=int, default=1)
-    ap.add_argument("--piece", type=int, default=16, choices=[8, 16], help="stream bytes each thread stages per chunk")
+    ap.add_argument("--piece", type=int, default=16, choices=[8, 16, 32, 64, 128],
+                    help="stream bytes each thread stages per chunk (> 16: cp.async into the idle buffer)")
     ap.add_argument("--npair", type=int, default=0, help="pair handlers for the N most frequent masks")
     ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
     ap.add_argument("--nstatic3", type=int, default=0)
