@@ -1121,6 +1121,9 @@ def main():
     ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
     ap.add_argument("--nstatic3", type=int, default=0)
     ap.add_argument("--split-tail", action="store_true", help="second g_k accumulator array: no reduction chain at record end")
+    ap.add_argument("--block2", type=int, default=0, help="2B: threads per CTA (0 = --block)")
+    ap.add_argument("--piece2", type=int, default=0, help="2B: stream bytes per thread and chunk (0 = --piece)")
+    ap.add_argument("--npre2", type=int, default=-1, help="2B: preload depth (-1 = --npre)")
     ap.add_argument("--sym2", type=int, default=0, help="2B: symmetry phases with a library of N leaf handlers (0 = off)")
     ap.add_argument("--sym3", type=int, default=0)
     ap.add_argument("--skeleton-weight", type=int, default=40)
@@ -1130,11 +1133,13 @@ def main():
                     "at least N times (no taken branch between two equal records)")
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
-        meta, _ = generate(name, args.out, args.block, args.min_blocks, args.nacc, args.ahead, not args.no_fuse,
-                           args.classes2 if name == "pip2b" else args.classes3, args.piece, npair=args.npair,
+        two = name == "pip2b"
+        meta, _ = generate(name, args.out, args.block2 if two and args.block2 else args.block, args.min_blocks, args.nacc,
+                           args.ahead, not args.no_fuse, args.classes2 if two else args.classes3,
+                           args.piece2 if two and args.piece2 else args.piece, npair=args.npair,
                            nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail,
                            sym=args.sym2 if name == "pip2b" else args.sym3, skeleton_weight=args.skeleton_weight,
-                           sib=args.sib, fall=args.fall, npre=args.npre)
+                           sib=args.sib, fall=args.fall, npre=args.npre2 if two and args.npre2 >= 0 else args.npre)
         print(meta)
 
 
