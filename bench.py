@@ -145,10 +145,35 @@ def run_reference_arm(args, workload, pos_mol, box):
         "e2e": {"value": value, "unit": "water-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """Rank 0's stdout must carry exactly ONE JSON line.  Libraries also write there (NCCL prints its version banner on
+    stdout at first communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON
+    line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -181,9 +206,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
-        # "NCCL version ..." on stdout) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peak_tf, _ = measure_fp64_peak()
 
@@ -297,7 +319,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, desc, kind = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers)
             line["cpu_baseline"] = {"value": v, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
