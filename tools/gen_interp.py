@@ -688,6 +688,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             return
         w(f"brx.idx {DISP}, TBL;")              # per-handler dispatch: ptxas can hoist the jump-table read
 
+    SEPTAIL = bool(int(os.environ.get("PIP_SEPTAIL", "0")))     # experiment: see block_handler
     TRICKLE = int(os.environ.get("PIP_TRICKLE", "4"))     # preload word pair q of the next record right after its last use
     FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
     ALIAS = int(os.environ.get("PIP_FAKE_ALIAS", "0"))          # timing experiment only: fold x/g onto N registers
@@ -814,6 +815,21 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             rops += [f"fma.rn.f64 %vc, {xk}, %u0, %vc;", f"fma.rn.f64 %vd, {xk}, %u1, %vd;",
                      "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u1, %gkb;",
                      "st.shared.f64 [%addr], %gk;", f"st.shared.f64 [%addr+{SG2 - SG}], %gkb;"]
+        elif SEPTAIL and static_k is None and len([a for a in acc if a in started]) >= 2:
+            # the last reduction level is not taken: the two partial sums go separately into the parent's two value
+            # accumulators and (back to back) into g_k -- one FP64 instruction more, one dependent level less
+            live = [a for a in acc if a in started]
+            while len(live) > 2:
+                nxt = []
+                for q in range(0, len(live) - 1, 2):
+                    rops.append(f"add.rn.f64 {live[q]}, {live[q]}, {live[q + 1]};")
+                    nxt.append(live[q])
+                if len(live) % 2:
+                    nxt.append(live[-1])
+                live = nxt
+            rops += [f"fma.rn.f64 %vc, {xk}, {live[0]}, %vc;", f"fma.rn.f64 %vd, {xk}, {live[1]}, %vd;",
+                     f"fma.rn.f64 %gk, %ac, {live[0]}, %gk;", f"fma.rn.f64 %gk, %ac, {live[1]}, %gk;",
+                     "st.shared.f64 [%addr], %gk;"]
         else:
             live = [a for a in acc if a in started]
             while len(live) > 1:
