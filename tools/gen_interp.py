@@ -16,6 +16,20 @@ the leaves cluster by block, so the padding costs only 11 % extra FMAs while the
 Only 32 (3B) / 19 (2B) distinct (block-mask) patterns occur.
 
 FP64 instructions per tuple: 2 * dense slots + 4 per node = ~79 k (3B), ~30 k (2B).
+
+Shipped configuration (mbpol_openmm_plugin_b200/build.py GEN_ARGS), all measured on B200:
+
+  * symmetry phases (`serialise_sym`): hydrogen / lone-pair swaps permute the variables; a node whose leaf coefficients are
+    invariant under a set of swaps is evaluated on the ORBIT SUMS of the variables, in a phase of the stream in which the
+    registers hold those sums -> 64 k (3B) / 22 k (2B) FP64 instructions; leaf handlers are specialised on arbitrary
+    register-slot sets chosen by an agglomerative merge (`merge_library`) instead of on symmetry blocks;
+  * SIBLING_d records (LEAVE_d + ENTER_d in one dispatch), look-ahead opcodes (LOOKAHEAD: the dispatch stays in the
+    uniform datapath, BRXU), a second copy of the leaf handlers that follow themselves (`fall`);
+  * the stream is staged in 16 KB chunks with cp.async straight into the idle shared-memory buffer (`piece` > 16);
+  * the 2B kernel runs 384 threads per CTA (168 registers -> 3 warps per scheduler).
+
+Everything else in this file (class split, PAIR / STATIC handlers, constant-bank stream, x_k prefetch, separate tail,
+...) is an experiment that was built, verified and timed, and lost (profiles/r01_microbench_*.log).
 """
 from __future__ import annotations
 
