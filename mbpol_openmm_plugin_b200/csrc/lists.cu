@@ -615,8 +615,9 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
             RES(halo, n + 1, unsigned char);
             RES(own3, n + 1, int);
             CK(cudaMemsetAsync(halo.ptr, 0, (size_t)n + 1, s));
-            mark_halo_kernel<<<blocks(slice_hi - slice_lo), 128, 0, s>>>(slice_lo, slice_hi, low3.as<int>(),
-                                                                         nbr3.as<int>(), halo.as<unsigned char>());
+            if (slice_hi > slice_lo)                     // (an empty owner range has no halo)
+                mark_halo_kernel<<<blocks(slice_hi - slice_lo), 128, 0, s>>>(slice_lo, slice_hi, low3.as<int>(),
+                                                                             nbr3.as<int>(), halo.as<unsigned char>());
             rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
                 posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), -1.0, c3sq, nbr2.as<int>(),
                 nbr3.as<int>(), low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(),

@@ -263,6 +263,36 @@ def test_sliced_list_build_matches_full(pbc):
 
 
 @pytest.mark.gpu
+def test_sliced_list_build_with_more_ranks_than_work():
+    """14 waters on 6 ranks: some owner ranges are empty or own no tuples; full and sliced evaluations still add up"""
+    import torch
+    g = load_golden("water14_xml")
+    pos = g["pos_mol"]
+    n = len(pos)
+    p = torch.as_tensor(pos.reshape(-1, 3)).cuda()
+    full = make_context(n, None, False)
+    full.setPositions(p)
+    e_full, f_full = full.getPotentialEnergy(), full.getForces()
+    world = 6
+    for sliced in (False, True):
+        e_sum, f_sum, nt = 0.0, torch.zeros_like(f_full), 0
+        for r in range(world):
+            ctx = make_context(n, None, False, rank=r, world=world)
+            ctx.setPositions(p)
+            ctx.getPotentialEnergy()
+            if sliced:
+                ctx.setPositions(p)
+                ctx.getPotentialEnergy()
+                nt += len(ctx.getTriplets())
+            e_sum += ctx.getPotentialEnergy()
+            f_sum += ctx.getForces()
+        assert abs(e_sum - e_full) <= 1e-11 * abs(e_full)
+        assert (f_sum - f_full).abs().max().item() < 1e-8
+        if sliced:
+            assert nt == len(full.getTriplets())
+
+
+@pytest.mark.gpu
 def test_sliced_list_build_refresh_and_opt_out(monkeypatch):
     """MBPOL_REPARTITION_EVERY=k: a full build (new balanced owner ranges) every k sliced ones; 0 disables slicing"""
     import torch
