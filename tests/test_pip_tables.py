@@ -46,7 +46,7 @@ def test_table_reproduces_reference_polynomial_values(name):
     ("pip3b", 1, {"npair": 8}), ("pip2b", 1, {"nstatic": 32}), ("pip3b", 1, {"nstatic": 48}),
     # symmetry phases (the shipped configuration: mbpol_openmm_plugin_b200/build.py GEN_ARGS) and their options
     ("pip2b", 1, {"sym": 12, "sib": True, "fall": 4, "npre": 4, "piece": 32, "block": 384}),
-    ("pip3b", 1, {"sym": 32, "sib": True, "fall": 4, "npre": 6, "piece": 64}),
+    ("pip3b", 1, {"sym": 32, "sib": True, "fall": 4, "npre": 8, "piece": 64}),
     ("pip2b", 1, {"sym": 16, "skeleton_weight": 0}), ("pip3b", 1, {"sym": 24, "skeleton_weight": 0})])
 def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
     """python interpreter of the packed streams (the same records the GPU kernels execute) vs the monomial definition;
@@ -81,7 +81,7 @@ def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
 def test_shipped_generator_settings_are_the_tested_ones():
     from mbpol_openmm_plugin_b200 import build
     a = build.GEN_ARGS
-    assert (a["sym2"], a["sym3"], a["sib"], a["fall"], a["npre"], a["piece"]) == (12, 32, True, 4, 6, 64)
+    assert (a["sym2"], a["sym3"], a["sib"], a["fall"], a["npre"], a["piece"]) == (12, 32, True, 4, 8, 64)
     assert (a["block2"], a["piece2"], a["npre2"]) == (384, 32, 4)
 
 

@@ -687,6 +687,20 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     cur_label = [None, None]
     fall_state = [None]
 
+    EARLY = bool(int(os.environ.get("PIP_EARLY_PRELOAD", "1")))
+    # ptxas cannot prove that the per-thread st.shared of g_k does not alias the stream window, so a preload that follows
+    # the store in program order can never be scheduled above it (and its latency ends up exposed, as R2UR /
+    # short-scoreboard stalls, at the end of the short handlers): with EARLY every handler issues its preloads of the
+    # next record BEFORE its store.
+
+    def early_preload(nwords, start=0):
+        """preload pairs start.. of the next record now; returns the `preloaded` argument for tail()"""
+        if not EARLY:
+            return start
+        for q in range(start, NPRE, 2):
+            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * q}];")
+        return NPRE
+
     def tail(nwords, preloaded=0):
         for q in range(preloaded, NPRE, 2):
             w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * q}];")
@@ -758,18 +772,20 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
             w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk{d}, [%addr];")
         w(f"mov.f64 %vs{d}, %vc; mov.f64 %vt{d}, %vd; mov.f64 %as{d}, %ac;")
         w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
+        pre = early_preload(2)
         w(f"mul.rn.f64 %ac, %ac, %xk{d};")
-        tail(2)
+        tail(2, pre)
     # ---- LEAVE_d
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_LEAVE + d - 1}:")
         head(2)
         w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
+        pre = early_preload(2)
         w("add.rn.f64 %w, %vc, %vd;")
         w(f"mov.f64 %ac, %as{d};")
         w(f"fma.rn.f64 %vc, %xk{d}, %w, %vs{d}; mov.f64 %vd, %vt{d};")
         w("fma.rn.f64 %gk, %ac, %w, %gk; st.shared.f64 [%addr], %gk;")
-        tail(2)
+        tail(2, pre)
 
     # ---- MASK_m and fused LEAFNODE_m
     def block_handler(label, m, fused, static_k=None):
@@ -876,6 +892,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                     if p2 + 1 < NPRE:
                         w(f"{LD}.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * p2}];")
                         done = p2 + 2
+            done = early_preload(nwords, done)
             for r in rops:
                 w(r)
             tail(nwords, done)
@@ -1002,11 +1019,12 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         else:
             w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
         w("add.rn.f64 %w, %vc, %vd;")
+        w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
+        pre = early_preload(2)
         w(f"fma.rn.f64 %vs{d}, %xk{d}, %w, %vs{d};")          # the parent's value, still saved
         w(f"fma.rn.f64 %gk, %as{d}, %w, %gk; st.shared.f64 [%addr], %gk;")
         w(f"mov.f64 %xk{d}, %xkb; mul.rn.f64 %ac, %as{d}, %xkb;")
-        w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
-        tail(2)
+        tail(2, pre)
     # ---- epilogue
     w("FINISH:")
     w("@!%valid bra DONE;")
