@@ -1,6 +1,7 @@
 """Micro-benchmark of the generated PIP evaluator cubins (development tool, GPU only).
 
-    python tools/pip_microbench.py build/variants/*/pip3b.cubin [--waves 8] [--block 256]
+    tools/mkvariant.sh TAG "ENV=.." [gen_interp.py arguments]        # -> build/mb/TAG/pip{2b,3b}.cubin
+    python tools/pip_microbench.py build/mb/*/pip3b.cubin [--waves 8]   # tuples = 148 SMs x CTA size x waves
 
 For every cubin: load it with the driver API, run {name}_eval on synthetic variables, check a few tuples against the
 reference polynomial (oracle/_ref, if present) and report time, tuples/s, issued FP64 instructions/s and the
@@ -71,7 +72,7 @@ def run(cubin, waves, block, reps, ref):
             ck(cu.cuFuncSetAttribute(fn, cu.CUfunction_attribute.CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem))
         fns.append(fn)
     block = int(meta.get("block", block))
-    n = 148 * 256 * waves
+    n = 148 * block * waves                 # whole waves of one CTA per SM, whatever the CTA size
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(nv, n, dtype=torch.float64, device="cuda", generator=g) * 1.2 + 0.1
     out = torch.zeros(nv + 1, n, dtype=torch.float64, device="cuda")
