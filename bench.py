@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 
 FLOP2, FLOP3 = 30601, 111818
 # dram__bytes_read.sum + dram__bytes_write.sum of one pip3b_eval launch inside this benchmark (7,103,084 trimers):
-# profiles/r01_ncu_pip3b_eval_sym_details.txt
-NCU_DRAM_BYTES_PER_TRIMER = (2.055654e9 + 2.059180e9) / 7103084
+# profiles/r01_ncu_pip3b_eval_final_details.txt
+NCU_DRAM_BYTES_PER_TRIMER = (2.054317e9 + 2.056927e9) / 7103084
 NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -304,7 +304,7 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "pip3b_eval", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                          # dram__bytes_read+write of one `ncu --set full` capture of this kernel (profiles/
-                         # r01_ncu_pip3b_eval_sym_details.txt: 4.11 GB for 7,103,084 trimers) scaled to this launch
+                         # r01_ncu_pip3b_eval_final_details.txt: 4.11 GB for 7,103,084 trimers) scaled to this launch
                          "traffic": acc["t3"] * NCU_DRAM_BYTES_PER_TRIMER, "traffic_unit": "bytes per launch",
                          "traffic_source": "ncu --set full, 579 B per trimer (algorithmic 584 B), scaled by trimers per launch",
                          "peak_source": "measured on this GPU: register-resident DFMA loop (mbpol_measure_fp64_peak); "
