@@ -560,7 +560,7 @@ def hexd(v):
 
 def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
                opaque=True, cmem=False, repeat=1, npair=0, combos=(), split_tail=False, phases=None, sib=False,
-               fall=(), npre=6):
+               fall=(), npre=6, fall_copies=2):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
@@ -683,6 +683,7 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
         w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}+{8 * nwords}];")
         next_xk()
 
+    FALL_COPIES = int(os.environ.get("PIP_FALL_COPIES", fall_copies))
     SELFBR = bool(int(os.environ.get("PIP_SELF_BRANCH", "0")))
     cur_label = [None, None]
     fall_state = [None]
@@ -981,10 +982,11 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     for mi, m in enumerate(masks):
         op = OP_MASK + len(masks) + mi
         if op in fall:
-            fall_state[0] = op
-            block_handler(f"H{op}", m, True)
-            fall_state[0] = None
-            block_handler(f"H{op}B", m, True)
+            # FALL_COPIES back-to-back copies: every copy but the last falls through into the next one when the next
+            # record has the same opcode (runs of 2, 3 and 4 equal records are the rule: symmetry-related siblings)
+            for c in range(FALL_COPIES):
+                fall_state[0] = op if c + 1 < FALL_COPIES else None
+                block_handler(f"H{op}" + ("" if c == 0 else "BCDEFGH"[c - 1]), m, True)
         else:
             block_handler(f"H{op}", m, True)
     for ci, (mi, kk) in enumerate(combos):
@@ -1093,7 +1095,7 @@ def count_fp64(recs, masks, blocks, combos=(), phases=None):
 
 def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
              npair=0, nstatic=0, split_tail=False, sym=0, skeleton_weight=40, sib=False,
-             fall=0, npre=6):
+             fall=0, npre=6, fall_copies=2):
     """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
     Returns (meta, [(words, masks) per class])."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
@@ -1134,7 +1136,7 @@ def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True,
         entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
         kl, sm = kernel_ptx(name, entry, symbol, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
                             npair=npair, combos=combos, split_tail=split_tail, phases=phases, sib=sib,
-                            fall=fall_ops if sym else (), npre=npre)
+                            fall=fall_ops if sym else (), npre=npre, fall_copies=fall_copies)
         lines += [""] + kl
         smem = max(smem, sm)
         streams.append((words, masks, combos))
@@ -1175,6 +1177,7 @@ def main():
     ap.add_argument("--sym2", type=int, default=0, help="2B: symmetry phases with a library of N leaf handlers (0 = off)")
     ap.add_argument("--sym3", type=int, default=0)
     ap.add_argument("--skeleton-weight", type=int, default=40)
+    ap.add_argument("--fall-copies", type=int, default=2, help="copies of a duplicated leaf handler")
     ap.add_argument("--npre", type=int, default=6, help="payload words of the next record every handler pre-loads")
     ap.add_argument("--sib", action="store_true", help="symmetry mode: fuse LEAVE_d + ENTER_d into SIBLING_d records")
     ap.add_argument("--fall", type=int, default=0, help="symmetry mode: duplicate leaf handlers that follow themselves "
@@ -1187,7 +1190,8 @@ def main():
                            args.piece2 if two and args.piece2 else args.piece, npair=args.npair,
                            nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail,
                            sym=args.sym2 if name == "pip2b" else args.sym3, skeleton_weight=args.skeleton_weight,
-                           sib=args.sib, fall=args.fall, npre=args.npre2 if two and args.npre2 >= 0 else args.npre)
+                           sib=args.sib, fall=args.fall, npre=args.npre2 if two and args.npre2 >= 0 else args.npre,
+                           fall_copies=args.fall_copies)
         print(meta)
 
 
