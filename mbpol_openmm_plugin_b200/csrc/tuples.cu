@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(128) dimer_vars_kernel(const double* __restric
         double xi = 0.0, ri = 0.0;                                      \
         if (active) {                                                   \
             const V3 d = s[p] - s[q];                                   \
-            const double r = sqrt(dot(d, d));                           \
-            ri = 1.0 / r;                                               \
+            const double d2 = dot(d, d);                                \
+            ri = rsqrt(d2);          /* one MUFU + Newton steps for */  \
+            const double r = d2 * ri; /* both r and 1/r (<= 2 ulp)  */  \
             const double e = exp((k) * ((r0) - r));                     \
             xi = (kind) ? e * ri : e;                                   \
         }                                                               \
@@ -288,8 +289,9 @@ __global__ void __launch_bounds__(128) trimer_vars_kernel(const double* __restri
         double xi = 0.0, ri = 0.0;                                       \
         if (active) {                                                    \
             const V3 d = (s[p] - s[q]) * NM_TO_A;                        \
-            const double r = sqrt(dot(d, d));                            \
-            ri = 1.0 / r;                                                \
+            const double d2 = dot(d, d);                                 \
+            ri = rsqrt(d2);           /* see dimer_vars_kernel */        \
+            const double r = d2 * ri;                                    \
             xi = exp(-(k) * (r - (r0)));                                 \
         }                                                                \
         x[(size_t)(i) * ld + t] = xi;                                    \
