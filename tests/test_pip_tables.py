@@ -106,3 +106,20 @@ def test_port_polynomial_matches_table(port):
         E, G = port.poly(order, x)
         Er, Gr = extract_pip.eval_table(t, x)
         assert abs(E - Er) <= 1e-12 * abs(Er) and np.abs(G - Gr).max() <= 1e-12 * np.abs(Gr).max()
+
+
+@pytest.mark.parametrize("name,macro,sites", [
+    ("pip2b", "MBPOL_2B_VARS", ["Oa", "Ha1", "Ha2", "Ob", "Hb1", "Hb2", "Xa1", "Xa2", "Xb1", "Xb2"]),
+    ("pip3b", "MBPOL_3B_VARS", ["Oa", "Ha1", "Ha2", "Ob", "Hb1", "Hb2", "Oc", "Hc1", "Hc2"])])
+def test_generator_and_cuda_kernels_agree_on_the_variable_table(name, macro, sites):
+    """the symmetry phases of the generator (tools/gen_interp.py::_sites) and the variable kernels (csrc/tuples.cu) must
+    mean the same site pair by variable i"""
+    import re
+    src = open(os.path.join(ROOT, "mbpol_openmm_plugin_b200", "csrc", "tuples.cu")).read()
+    body = src[src.index("#define " + macro):]
+    body = body[:body.index("\n\n")]
+    rows = re.findall(r"V\((\d+),(?:\s*\d+,)?\s*\w+,\s*\w+,\s*(\d+),\s*(\d+)\)", body)
+    table = {int(i): frozenset((sites[int(p)], sites[int(q)])) for i, p, q in rows}
+    pairs, _ = gen_interp._sites(name)
+    assert sorted(table) == list(range(len(pairs)))
+    assert [table[i] for i in range(len(pairs))] == [frozenset(p) for p in pairs]
