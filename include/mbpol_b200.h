@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MBPOL_ABI_VERSION 1
+#define MBPOL_ABI_VERSION 2
 
 /* error codes */
 #define MBPOL_OK            0
@@ -32,6 +32,7 @@ extern "C" {
 #define MBPOL_EBOX         (-3)   /* periodic box smaller than twice the cutoff (MBPolReferenceKernels.cpp:384-391) */
 #define MBPOL_ECHANGED     (-4)   /* number of molecules changed (MBPolReferenceKernels.cpp:402-403) */
 #define MBPOL_ENOMEM       (-5)
+#define MBPOL_ECOMM        (-6)   /* NCCL missing or a collective failed */
 
 /* nonbonded method: values of MBPolTwoBodyForce::NonbondedMethod (openmmapi/include/openmm/MBPolTwoBodyForce.h:62-74) */
 #define MBPOL_NOCUTOFF            0   /* treated as CutoffNonPeriodic with an infinite cutoff */
@@ -72,6 +73,11 @@ typedef struct mbpol_stats {
     float   ms_lists, ms_2b, ms_3b, ms_reduce;   /* device time of the stages (CUDA events), 0 if timing disabled */
     float   ms_pip_2b, ms_pip_3b;                /* the polynomial kernels alone (the roofline kernels)             */
     int64_t n_launches;     /* kernels launched by the last mbpol_eval (library-internal CUB passes counted once each) */
+    float   ms_bcast, ms_comm_reduce;            /* mbpol_eval_distributed: the two collectives (CUDA events)        */
+    int32_t lists_sliced;   /* 1: the lists of this evaluation hold only this rank's tuples (n_pairs / n_triplets = -1) */
+    int32_t lists_reused;   /* 1: the neighbour rows of an earlier evaluation were reused (Verlet skin / KEEP_LISTS)     */
+    int64_t n_repartitions; /* full list builds with a fresh owner balance since mbpol_set_partition                  */
+    int64_t n_row_builds;   /* neighbour-row builds since the context was created (skin reuse skips them)             */
 } mbpol_stats;
 
 /* replaces CalcMBPol*ForceKernel::initialize (MBPolReferenceKernels.cpp:341-360, 430-449) */
@@ -132,6 +138,50 @@ int  mbpol_get_triplets(mbpol_ctx* ctx, int32_t* out /* n x 3 */, size_t* n);
 
 int  mbpol_get_stats(const mbpol_ctx* ctx, mbpol_stats* out);
 int  mbpol_set_timing(mbpol_ctx* ctx, int32_t enabled);   /* record per-stage CUDA events (adds a sync per eval) */
+
+/* ---- energies without a host synchronisation -------------------------------------------------------------------
+ * mbpol_eval with energy == NULL leaves {E_2B, E_3B} of the call in device memory.  mbpol_energy_device returns that
+ * DEVICE pointer (3 doubles: E_2B, E_3B, E_1B of the last evaluations; valid in stream order after the call);
+ * mbpol_get_energy copies them to the host (synchronises `stream`). */
+const double* mbpol_energy_device(const mbpol_ctx* ctx);
+int  mbpol_get_energy(mbpol_ctx* ctx, double energy[3], void* stream);
+
+/* ---- OpenMM CUDA platform buffers (the ownership row of SURVEY.md 8b) ---------------------------------------------
+ * What CudaCalcMBPol{Two,Three}BodyForceKernel::execute works on (platforms/cuda/src/CudaMBPolKernels.cpp:278-304,
+ * 1976-2005): cu.getPosq() (real4, or double4 with CudaPrecision=double), in OpenMM's REORDERED atom order
+ * (cu.getAtomIndex(): slot -> original particle index), cu.getForce() (int64 fixed point, value * 2^32, SoA
+ * [x: padded][y: padded][z: padded], same slot order) and cu.getEnergyBuffer() (element 0 receives += energy; double
+ * in the double and mixed precision modes, float in single).  The particle indices given to mbpol_create are ORIGINAL
+ * indices, as in the MBPol*Force objects.  All pointers DEVICE; atom_index may be NULL (identity order); force_buffer
+ * and energy_buffer may be NULL.  Nothing is copied to the host and the stream is not synchronised: execute() returns
+ * 0.0 on the CUDA platform (CudaMBPolKernels.cpp:303). */
+int  mbpol_eval_openmm(mbpol_ctx* ctx, const void* posq, int32_t posq_is_double, const int32_t* atom_index,
+                       int32_t num_atoms, long long* force_buffer, int32_t padded_num_atoms, void* energy_buffer,
+                       int32_t energy_is_double, uint32_t flags, void* stream);
+
+/* ---- multi-GPU behind the C ABI: NCCL broadcast / reduce (north_star (3)) ----------------------------
+ * One process or thread per GPU, one context per rank.  Rank 0 obtains a 128-byte id (ncclGetUniqueId), the host
+ * program ships it to the other ranks (MPI, a file, torch.distributed's store ...), every rank calls
+ * mbpol_comm_init_rank (ncclCommInitRank on the context's device + mbpol_set_partition(rank, world)).
+ * mbpol_comm_adopt uses an ncclComm_t the host program already owns instead (rank / world are read from it; it is not
+ * destroyed with the context).  NCCL is bound at run time (libnccl.so.2); MBPOL_ECOMM if it is not there. */
+#define MBPOL_COMM_ID_BYTES 128
+int  mbpol_comm_unique_id(void* id_out /* MBPOL_COMM_ID_BYTES */);
+int  mbpol_comm_init_rank(mbpol_ctx* ctx, const void* id, int32_t rank, int32_t world);
+int  mbpol_comm_adopt(mbpol_ctx* ctx, void* nccl_comm);
+int  mbpol_comm_destroy(mbpol_ctx* ctx);
+
+/* One distributed evaluation, all ranks in lockstep on `stream`:
+ *   ncclBroadcast(pos_nm) from rank 0  ->  lists + 2B + 3B of this rank's owner range  ->  ONE grouped NCCL reduce of
+ *   the force array and the two energies to rank 0 (MBPOL_DIST_ALLREDUCE: all-reduce, every rank receives them, e.g.
+ *   for a replicated integrator; MBPOL_DIST_NO_BCAST: positions are already identical on every rank).
+ *   pos_nm : DEVICE, n_particles x 3; input on rank 0, overwritten by the broadcast elsewhere
+ *   force  : DEVICE, n_particles x 3; OVERWRITTEN with the summed forces on the receiving rank(s); may be NULL elsewhere
+ *   energy : HOST, 2 doubles {E_2B, E_3B}, written on the receiving rank(s); NULL = no host synchronisation */
+#define MBPOL_DIST_ALLREDUCE 16u
+#define MBPOL_DIST_NO_BCAST  32u
+int  mbpol_eval_distributed(mbpol_ctx* ctx, double* pos_nm, double* force, double* energy, uint32_t flags,
+                            void* stream);
 
 /* ---- lower-level entry points used by the unit tests and the roofline benchmark ------------------------------- */
 

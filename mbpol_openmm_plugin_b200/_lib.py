@@ -11,10 +11,12 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmbpol_b200.so")
 
-ABI_VERSION = 1
-OK, EINVAL, ECUDA, EBOX, ECHANGED, ENOMEM = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 2
+OK, EINVAL, ECUDA, EBOX, ECHANGED, ENOMEM, ECOMM = 0, -1, -2, -3, -4, -5, -6
 NOCUTOFF, CUTOFF_PERIODIC, CUTOFF_NONPERIODIC = 0, 1, 2
 DO_2B, DO_3B, KEEP_LISTS, OVERWRITE_FORCES = 1, 2, 4, 8
+DIST_ALLREDUCE, DIST_NO_BCAST = 16, 32
+COMM_ID_BYTES = 128
 FLOP_PER_DIMER, FLOP_PER_TRIMER = 30601, 111818
 
 # every symbol include/mbpol_b200.h declares (checked by tests/test_abi.py)
@@ -23,6 +25,8 @@ EXPORTS = (
     "mbpol_set_partition", "mbpol_eval", "mbpol_eval_host", "mbpol_add_forces_fixed_point", "mbpol_get_pairs",
     "mbpol_get_triplets", "mbpol_get_stats", "mbpol_set_timing", "mbpol_pip_eval", "mbpol_eval_tuples",
     "mbpol_measure_fp64_peak", "mbpol_pip_instruction_count", "mbpol_eval_onebody", "mbpol_eval_onebody_host",
+    "mbpol_energy_device", "mbpol_get_energy", "mbpol_eval_openmm", "mbpol_comm_unique_id", "mbpol_comm_init_rank",
+    "mbpol_comm_adopt", "mbpol_comm_destroy", "mbpol_eval_distributed",
 )
 
 
@@ -35,7 +39,9 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_triplets", C.c_int64), ("n_pairs_owned", C.c_int64),
                 ("n_triplets_owned", C.c_int64), ("ms_lists", C.c_float), ("ms_2b", C.c_float), ("ms_3b", C.c_float),
-                ("ms_reduce", C.c_float), ("ms_pip_2b", C.c_float), ("ms_pip_3b", C.c_float), ("n_launches", C.c_int64)]
+                ("ms_reduce", C.c_float), ("ms_pip_2b", C.c_float), ("ms_pip_3b", C.c_float), ("n_launches", C.c_int64),
+                ("ms_bcast", C.c_float), ("ms_comm_reduce", C.c_float), ("lists_sliced", C.c_int32),
+                ("lists_reused", C.c_int32), ("n_repartitions", C.c_int64), ("n_row_builds", C.c_int64)]
 
 
 class MBPolError(RuntimeError):
@@ -80,9 +86,18 @@ def load():
     L.mbpol_eval_tuples.argtypes = [C.c_int, dp, C.c_int32, vp, C.c_int64, C.POINTER(C.c_double), C.c_int, dp, dp, vp]
     L.mbpol_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mbpol_pip_instruction_count.argtypes = [C.c_int]
+    L.mbpol_energy_device.argtypes = [vp]
+    L.mbpol_energy_device.restype = C.c_void_p
+    L.mbpol_get_energy.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.mbpol_eval_openmm.argtypes = [vp, dp, C.c_int32, dp, C.c_int32, dp, C.c_int32, dp, C.c_int32, C.c_uint32, vp]
+    L.mbpol_comm_unique_id.argtypes = [C.c_char_p]
+    L.mbpol_comm_init_rank.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    L.mbpol_comm_adopt.argtypes = [vp, vp]
+    L.mbpol_comm_destroy.argtypes = [vp]
+    L.mbpol_eval_distributed.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("mbpol_destroy", "mbpol_last_error"):
+        if name not in ("mbpol_destroy", "mbpol_last_error", "mbpol_energy_device"):
             fn.restype = C.c_int
     _lib = L
     return L

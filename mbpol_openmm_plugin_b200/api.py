@@ -347,11 +347,26 @@ class MBPolContext:
         self._flags |= kernel._flag
 
     def _update_parameters(self, force):
+        # The forces of one context share one engine, hence one molecule table.  An update of one force is pushed at
+        # once; that all forces list the same molecules again (what the constructor enforces) is checked at the next
+        # evaluation, so that the forces can be updated one after the other.
         self.engine.update_particles(force._indices())
+        self._check_same_molecules = True
+
+    def _same_molecules_or_raise(self):
+        ref = self._f2 or self._f3 or self._f1
+        for other in (self._f1, self._f2, self._f3):
+            if other is not None and other is not ref and not np.array_equal(other._indices(), ref._indices()):
+                raise MBPolError(_lib.EINVAL, "updateParametersInContext: the forces of this context no longer list "
+                                              "the same molecules")
+        self.engine.update_particles(ref._indices())
+        self._check_same_molecules = False
 
     def _execute(self, flags):
         if self._pos is None:
             raise MBPolError(_lib.EINVAL, "positions have not been set")
+        if getattr(self, "_check_same_molecules", False):
+            self._same_molecules_or_raise()
         host = isinstance(self._pos, np.ndarray)
         stream = None
         many = flags & (_lib.DO_2B | _lib.DO_3B)

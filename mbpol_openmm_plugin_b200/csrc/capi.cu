@@ -11,55 +11,28 @@
 #include <cstring>
 #include <vector>
 
-#include "lists.h"
+#include "context.h"
 
-using namespace mbpol;
-
-struct mbpol_ctx {
-    int device = 0;
-    int n_mol = 0, n_particles = 0;
-    double cut2 = 1e10, cut3 = 1e10;
-    int method2 = MBPOL_CUTOFF_NONPERIODIC, method3 = MBPOL_CUTOFF_NONPERIODIC;
-    double box[3] = {0, 0, 0};
-    int rank = 0, world = 1;
-    // multi-GPU: owner range of this rank from the last FULL list build.  While it is valid, list builds are SLICED:
-    // only this rank's owners and their halo get neighbour rows (TupleLists::build).  Every rank refreshes it at the
-    // same evaluation count, from the same positions, so the ranges always tile [0, n_mol).
-    bool slice_valid = false, slice_want2 = false, slice_want3 = false, slice_periodic = false;
-    int slice_lo = 0, slice_hi = 0, slice_age = 0, repartition_every = 50;
-    int64_t full_pairs = 0, full_trips = 0;
-    bool lists_valid = false;
-    bool timing = false;
-    std::string err;
-    mbpol_stats stats{};
-
-    DeviceBuf idx;
-    TupleLists lists;
-    ContributionIndex ci2, ci3;
-    DeviceBuf x2, r2, o2, e2, f2, x3, r3, o3, e3, f3;
-    DeviceBuf f_mol, e_partial, d_energy, pos_stage, force_stage, e1;
-    cudaEvent_t ev[6] = {}, evp[4] = {};      // stage events; events around the two polynomial kernels
-    bool f_mol_valid = false;
-};
-
-static thread_local std::string g_create_error;
+thread_local std::string g_create_error;
 
 namespace {
-
-int fail(mbpol_ctx* c, int code, const std::string& msg) {
-    if (c) c->err = msg; else g_create_error = msg;
-    return code;
-}
-
-#define CKC(call)                                                                                  \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(ctx, MBPOL_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
 
 inline int64_t round_up(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
 
 bool is_periodic(int method) { return method == MBPOL_CUTOFF_PERIODIC; }
+
+// Every particle may belong to one molecule only: the force scatter and the one-body kernel write force[p] without
+// atomics (the reference accumulates serially, so it has no such constraint to state).  Returns an error text or "".
+std::string check_indices(const int32_t* idx, int64_t n_mol, int64_t n_particles) {
+    std::vector<char> seen((size_t)n_particles, 0);
+    for (int64_t i = 0; i < 3 * n_mol; ++i) {
+        const int32_t p = idx[i];
+        if (p < 0 || p >= n_particles) return "particle index out of range";
+        if (seen[p]) return "particle index " + std::to_string(p) + " listed more than once";
+        seen[p] = 1;
+    }
+    return "";
+}
 double eff_cutoff(int method, double c) { return method == MBPOL_NOCUTOFF ? 1e10 : c; }
 
 // One body order over the owned tuple range.  order = 2 | 3.
@@ -126,16 +99,25 @@ int eval_pass(mbpol_ctx* ctx, const double* pos, bool want2, bool want3, bool pe
         if (want3 && (rc = check_box(ctx, c3))) return rc;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[0], s);
+    NvtxRange r_lists("mbpol:lists");
     const bool reuse = (flags & MBPOL_KEEP_LISTS) && ctx->lists_valid && ctx->lists.has2 == want2 &&
                        ctx->lists.has3 == want3;
     if (!reuse) {
         ctx->lists_valid = false;
+        // While the balance of the last repartition is valid, every build is requested SLICED.  All ranks take this
+        // decision from the same counters, so their owner ranges always tile [0, n_mol).
         const bool slice = ctx->world > 1 && ctx->slice_valid && ctx->slice_want2 == want2 && ctx->slice_want3 == want3 &&
                            ctx->slice_periodic == periodic && ctx->slice_age < ctx->repartition_every;
         if ((rc = ctx->lists.build(pos, ctx->idx.as<int32_t>(), ctx->n_mol, ctx->box, periodic, c2, c3, want2, want3, s,
                                    ctx->err, slice ? ctx->slice_lo : 0, slice ? ctx->slice_hi : -1)))
             return rc;
-        if (ctx->lists.sliced) {
+        if (slice) {
+            // A requested slice may still come back as full lists on THIS rank only (a neighbour row overflowed the
+            // fixed stride, or the range is all of [0, n)).  The owner range and the refresh schedule must not move:
+            // the other ranks keep theirs.  Only the offsets of the range inside the full lists are looked up.
+            if (!ctx->lists.sliced &&
+                (rc = ctx->lists.partition(ctx->rank, ctx->world, s, ctx->err, ctx->slice_lo, ctx->slice_hi)))
+                return rc;
             ++ctx->slice_age;
         } else {
             if ((rc = ctx->lists.partition(ctx->rank, ctx->world, s, ctx->err))) return rc;
@@ -146,34 +128,48 @@ int eval_pass(mbpol_ctx* ctx, const double* pos, bool want2, bool want3, bool pe
             ctx->slice_want3 = want3;
             ctx->slice_periodic = periodic;
             ctx->slice_age = 0;
-            ctx->full_pairs = ctx->lists.n_pairs;
-            ctx->full_trips = ctx->lists.n_trips;
+            ++ctx->n_repartitions;
         }
         ctx->lists_valid = true;
     }
+    r_lists.end();
     if (ctx->timing) cudaEventRecord(ctx->ev[1], s);
     if (want2) {
+        NvtxRange r("mbpol:2B");
         if ((rc = run_order(ctx, 2, pos, s, !fmol_started))) return rc;
         fmol_started = true;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[2], s);
     if (want3) {
+        NvtxRange r("mbpol:3B");
         if ((rc = run_order(ctx, 3, pos, s, !fmol_started))) return rc;
         fmol_started = true;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[3], s);
+    // after a sliced build only this rank's tuples exist: the box-wide totals are then unknown (-1), not stale
     if (want2) {
-        ctx->stats.n_pairs = ctx->lists.sliced ? ctx->full_pairs : ctx->lists.n_pairs;
+        ctx->stats.n_pairs = ctx->lists.sliced ? -1 : ctx->lists.n_pairs;
         ctx->stats.n_pairs_owned = ctx->lists.own_p1 - ctx->lists.own_p0;
     }
     if (want3) {
-        ctx->stats.n_triplets = ctx->lists.sliced ? ctx->full_trips : ctx->lists.n_trips;
+        ctx->stats.n_triplets = ctx->lists.sliced ? -1 : ctx->lists.n_trips;
         ctx->stats.n_triplets_owned = ctx->lists.own_t1 - ctx->lists.own_t0;
     }
     return MBPOL_OK;
 }
 
 }  // namespace
+
+int mbpol_collect_timing(mbpol_ctx* ctx) {
+    CKC(cudaEventSynchronize(ctx->ev[4]));
+    cudaEventElapsedTime(&ctx->stats.ms_lists, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_2b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.ms_3b, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->stats.ms_reduce, ctx->ev[3], ctx->ev[4]);
+    if (ctx->timed2) cudaEventElapsedTime(&ctx->stats.ms_pip_2b, ctx->evp[0], ctx->evp[1]);
+    if (ctx->timed3) cudaEventElapsedTime(&ctx->stats.ms_pip_3b, ctx->evp[2], ctx->evp[3]);
+    return MBPOL_OK;
+}
 
 extern "C" {
 
@@ -187,9 +183,10 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
         if (m < 0 || m > 2) return fail(nullptr, MBPOL_EINVAL, "mbpol_create: unknown nonbonded method");
     if (!(cfg->cutoff_2b_nm > 0) || !(cfg->cutoff_3b_nm > 0))
         return fail(nullptr, MBPOL_EINVAL, "mbpol_create: cutoffs must be positive");
-    for (int64_t i = 0; i < 3LL * cfg->n_molecules; ++i)
-        if (cfg->particle_indices[i] < 0 || cfg->particle_indices[i] >= cfg->n_particles)
-            return fail(nullptr, MBPOL_EINVAL, "mbpol_create: particle index out of range");
+    {
+        const std::string bad = check_indices(cfg->particle_indices, cfg->n_molecules, cfg->n_particles);
+        if (!bad.empty()) return fail(nullptr, MBPOL_EINVAL, "mbpol_create: " + bad);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -220,22 +217,23 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
     if (ctx->n_mol > 0 && cudaMemcpy(ctx->idx.ptr, cfg->particle_indices, sizeof(int32_t) * 3 * (size_t)ctx->n_mol,
                                      cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(MBPOL_ECUDA, "copying particle indices failed");
-    cudaMemset(ctx->d_energy.ptr, 0, 2 * sizeof(double));
+    cudaMemset(ctx->d_energy.ptr, 0, 4 * sizeof(double));
     if (const char* f = getenv("MBPOL_FORCE_TWO_PASS")) ctx->lists.force_two_pass = f[0] == '1';
     if (const char* f = getenv("MBPOL_REPARTITION_EVERY")) ctx->repartition_every = atoi(f);   // 0: never slice
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evp) cudaEventCreate(&e);
+    for (auto& e : ctx->evc) cudaEventCreate(&e);
     *out = ctx;
     return MBPOL_OK;
 }
 
 void mbpol_destroy(mbpol_ctx* ctx) {
     if (!ctx) return;
+    mbpol_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
-    for (auto& e : ctx->ev)
-        if (e) cudaEventDestroy(e);
-    for (auto& e : ctx->evp)
-        if (e) cudaEventDestroy(e);
+    for (auto* set : {ctx->ev + 0, ctx->evp + 0, ctx->evc + 0})
+        for (int i = 0; i < (set == ctx->ev ? 6 : 4); ++i)
+            if (set[i]) cudaEventDestroy(set[i]);
     delete ctx;
 }
 
@@ -245,9 +243,10 @@ int mbpol_update_particles(mbpol_ctx* ctx, int32_t n_molecules, const int32_t* p
     if (!ctx || !particle_indices) return fail(ctx, MBPOL_EINVAL, "mbpol_update_particles: null argument");
     if (n_molecules != ctx->n_mol)
         return fail(ctx, MBPOL_ECHANGED, "updateParametersInContext: The number of particles has changed");
-    for (int64_t i = 0; i < 3LL * n_molecules; ++i)
-        if (particle_indices[i] < 0 || particle_indices[i] >= ctx->n_particles)
-            return fail(ctx, MBPOL_EINVAL, "mbpol_update_particles: particle index out of range");
+    {
+        const std::string bad = check_indices(particle_indices, n_molecules, ctx->n_particles);
+        if (!bad.empty()) return fail(ctx, MBPOL_EINVAL, "mbpol_update_particles: " + bad);
+    }
     CKC(cudaSetDevice(ctx->device));
     CKC(cudaMemcpy(ctx->idx.ptr, particle_indices, sizeof(int32_t) * 3 * (size_t)n_molecules, cudaMemcpyHostToDevice));
     ctx->lists_valid = false;
@@ -299,21 +298,29 @@ int mbpol_eval(mbpol_ctx* ctx, const double* pos_nm, double* force, double* ener
         ctx->f_mol_valid = started;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[4], s);
+    ctx->timed2 = want2 && ctx->stats.n_pairs_owned > 0;
+    ctx->timed3 = want3 && ctx->stats.n_triplets_owned > 0;
     if (energy) {
         CKC(cudaMemcpyAsync(energy, ctx->d_energy.ptr, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
         CKC(cudaStreamSynchronize(s));
     }
-    if (ctx->timing) {
-        CKC(cudaEventSynchronize(ctx->ev[4]));
-        cudaEventElapsedTime(&ctx->stats.ms_lists, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&ctx->stats.ms_2b, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&ctx->stats.ms_3b, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&ctx->stats.ms_reduce, ctx->ev[3], ctx->ev[4]);
-        if (want2 && ctx->stats.n_pairs_owned > 0) cudaEventElapsedTime(&ctx->stats.ms_pip_2b, ctx->evp[0], ctx->evp[1]);
-        if (want3 && ctx->stats.n_triplets_owned > 0) cudaEventElapsedTime(&ctx->stats.ms_pip_3b, ctx->evp[2], ctx->evp[3]);
-    }
     ctx->stats.n_launches = g_launches;
+    ctx->stats.lists_sliced = ctx->lists.sliced;
+    ctx->stats.n_repartitions = ctx->n_repartitions;
+    ctx->stats.n_row_builds = ctx->lists.n_row_builds;
+    ctx->stats.lists_reused = ctx->lists.rows_reused;
+    if (ctx->timing && !ctx->timing_defer_sync && (rc = mbpol_collect_timing(ctx))) return rc;
     CKC(cudaGetLastError());
+    return MBPOL_OK;
+}
+
+const double* mbpol_energy_device(const mbpol_ctx* ctx) { return ctx ? ctx->d_energy.as<double>() : nullptr; }
+
+int mbpol_get_energy(mbpol_ctx* ctx, double energy[3], void* stream) {
+    if (!ctx || !energy) return fail(ctx, MBPOL_EINVAL, "mbpol_get_energy: null argument");
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaMemcpyAsync(energy, ctx->d_energy.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CKC(cudaStreamSynchronize((cudaStream_t)stream));
     return MBPOL_OK;
 }
 

@@ -408,11 +408,13 @@ __global__ void segment_offsets_kernel(int n, int64_t count, const int32_t* __re
 // owner slice of `rank`: boundaries by binary search on the cumulative work, then the matching tuple offsets
 __global__ void partition_kernel(int n, int rank, int world, const int64_t* __restrict__ W,
                                  const int64_t* __restrict__ pstart, const int64_t* __restrict__ qstart,
-                                 const int64_t* __restrict__ tstart, int64_t* __restrict__ out /* 6 */) {
+                                 const int64_t* __restrict__ tstart, int64_t* __restrict__ out /* 6 */, int fixed_lo,
+                                 int fixed_hi) {
     if (threadIdx.x > 1) return;
     const int r = rank + threadIdx.x;                 // thread 0: lower bound, thread 1: upper bound
     int b;
-    if (r <= 0) b = 0;
+    if (fixed_hi >= 0) b = threadIdx.x ? fixed_hi : fixed_lo;     // keep the owner range of an earlier balance
+    else if (r <= 0) b = 0;
     else if (r >= world) b = n;
     else {
         const double target = (double)W[n] * r / world;
@@ -483,6 +485,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     // and the 0.45 nm halo below them -- instead of all n; the lists then hold exactly this rank's tuples
     bool slice = slice_hi >= 0 && !force_two_pass && (slice_lo > 0 || slice_hi < n_mol);
     sliced = false;
+    rows_reused = false;
     n_pairs = n_trips = n_qpairs = 0;
     has2 = want2;
     has3 = want3;
@@ -534,6 +537,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     }
 
     // ---- cells --------------------------------------------------------------------------------------------------
+    ++n_row_builds;
     RES(cell_of, n, int);
     RES(cell_count, ncell + 1, int);
     RES(cell_start64, ncell + 1, int64_t);
@@ -682,8 +686,10 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     return MBPOL_OK;
 }
 
-int TupleLists::partition(int rank, int world, cudaStream_t s, std::string& err) {
+int TupleLists::partition(int rank, int world, cudaStream_t s, std::string& err, int fixed_lo, int fixed_hi) {
     // Owner ranges [I0, I1) with equal cumulative work; every rank computes the same boundaries from the same lists.
+    // With fixed_hi >= 0 the range [fixed_lo, fixed_hi) of an earlier balance is kept and only its pair / triplet
+    // offsets in the (full) lists of this build are looked up.
     own_p0 = own_t0 = 0;
     own_p1 = n_pairs;
     own_t1 = n_trips;
@@ -693,7 +699,7 @@ int TupleLists::partition(int rank, int world, cudaStream_t s, std::string& err)
     int rc;
     if ((rc = scratch.reserve(sizeof(int64_t) * 6, err))) return rc;
     partition_kernel<<<1, 32, 0, s>>>(n, rank, world, weight.as<int64_t>(), pstart.as<int64_t>(), qstart.as<int64_t>(),
-                                      tstart.as<int64_t>(), scratch.as<int64_t>()); MBPOL_COUNT_LAUNCH(1);
+                                      tstart.as<int64_t>(), scratch.as<int64_t>(), fixed_lo, fixed_hi); MBPOL_COUNT_LAUNCH(1);
     int64_t h[6];
     CK(cudaMemcpyAsync(h, scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -36,6 +36,8 @@ struct TupleLists {
     bool force_two_pass = false;     // MBPOL_FORCE_TWO_PASS=1: skip the fixed-stride fast path (tests cover both)
     bool used_fast_rows = false;
     bool sliced = false;             // the last build covered only this rank's owners [own_i0, own_i1) + their halo
+    bool rows_reused = false;        // the last build filtered the skin rows of an earlier build instead of scanning cells
+    int64_t n_row_builds = 0;        // cell-grid + neighbour-row scans so far
     int64_t n_pairs = 0, n_qpairs = 0, n_trips = 0;
     // owner partition of this rank: molecules [own_i0, own_i1), pairs [own_p0, own_p1), triplets [own_t0, own_t1)
     int own_i0 = 0, own_i1 = 0;
@@ -49,7 +51,7 @@ struct TupleLists {
     int build(const double* pos, const int32_t* idx, int n_mol, const double box[3], bool periodic, double cut2,
               double cut3, bool want2, bool want3, cudaStream_t s, std::string& err, int slice_lo = 0,
               int slice_hi = -1);
-    int partition(int rank, int world, cudaStream_t s, std::string& err);
+    int partition(int rank, int world, cudaStream_t s, std::string& err, int fixed_lo = -1, int fixed_hi = -1);
 };
 
 // For every molecule m: the list of (local tuple, role) entries that put force on it, in ascending (tuple, role)

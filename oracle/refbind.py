@@ -248,6 +248,23 @@ def have_port():
     return os.path.exists(PORT_SO)
 
 
+def eval_parallel(oracle, order, pos, idx, tuples, box, pbc, threads=None, chunk=20000):
+    """E and F of a long tuple list, the checker fanned out over host threads (ctypes releases the GIL; the reference
+    code keeps no state between calls).  Chunks are summed in list order, so the result does not depend on `threads`.
+    Used for the whole-box comparison at 262,144 waters (about 330 core-seconds) and by bench.py's reference arm."""
+    from concurrent.futures import ThreadPoolExecutor
+    threads = threads or len(os.sched_getaffinity(0))
+    fn = oracle.eval_2b if order == 2 else oracle.eval_3b
+    tuples = np.ascontiguousarray(tuples)
+    parts = [tuples[i:i + chunk] for i in range(0, len(tuples), chunk)]
+    e_tot, f_tot = 0.0, np.zeros_like(_f64(pos))
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        for res in ex.map(lambda t: fn(pos, idx, t, box, pbc)[:2], parts):
+            e_tot += res[0]
+            f_tot += res[1]
+    return e_tot, f_tot
+
+
 def best():
     """The strongest checker available: the reference's own code if it was built, else the port."""
     return Ref() if have_ref() else Port()

@@ -53,9 +53,18 @@ def test_context_from_pdb(tmp_path):
     f = ctx.getForces().reshape(14, 4, 3)
     assert np.all(f[:, 3] == 0.0)
     many = ctx.energies["CalcMBPolTwoBodyForce"] + ctx.energies["CalcMBPolThreeBodyForce"]
-    assert abs(many - (float(g["e2"]) + float(g["e3"]))) < 2.0     # kJ/mol: rounding of the PDB coordinates only
-    # the one-body surface is stiff (~1e3 kJ/mol/A^2 per O-H): compare it on the rounded coordinates themselves
-    from oracle.refbind import best
-    e1, _ = best().eval_1b(pdb.positions, np.asarray(pdb.water_indices()), None, False)
+    # every term against the oracle on the rounded PDB coordinates themselves: lists bit-exact, E 1e-9, F 1e-6
+    from oracle.refbind import best, canonical
+    o = best()
+    widx = np.asarray(pdb.water_indices())
+    posO = pdb.positions[widx[:, 0]].copy()
+    pairs, trips = canonical(o.pairs(posO, None, False, 0.65)), canonical(o.triplets(posO, None, False, 0.45))
+    assert np.array_equal(ctx.getPairs(), pairs) and np.array_equal(ctx.getTriplets(), trips)
+    e2, f2 = o.eval_2b(pdb.positions, widx, pairs, None, False)[:2]
+    e3, f3 = o.eval_3b(pdb.positions, widx, trips, None, False)[:2]
+    e1, f1 = o.eval_1b(pdb.positions, widx, None, False)
+    assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2) <= 1e-9 * abs(e2)
+    assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3) <= 1e-9 * abs(e3)
     assert abs(ctx.energies["CalcMBPolOneBodyForce"] - e1) <= 1e-9 * abs(e1)
+    assert np.abs(ctx.getForces() - (f1 + f2 + f3)).max() < 1e-6
     assert abs(e - (many + e1)) < 1e-9

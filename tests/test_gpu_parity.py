@@ -39,9 +39,10 @@ def test_golden_fixture_host_arrays(case):
 
 
 @pytest.mark.parametrize("case", ["water14_xml", "water256_bulk", "test_trimer_pbc_shifted"])
-def test_golden_fixture_device_tensors_and_m_sites(case):
+def test_golden_fixture_device_tensors_and_m_sites(case, checker):
     """Device-resident positions, 4 particles per molecule (O,H1,H2,M) offset by +25 nm like
-    platforms/cuda/tests/TestCudaMBPolThreeBodyForce.cpp:66-150: M sites get exactly zero force."""
+    platforms/cuda/tests/TestCudaMBPolThreeBodyForce.cpp:66-150: M sites get exactly zero force.  Periodic cases are
+    evaluated on a translated image of the whole system; the oracle is run on the SAME translated coordinates."""
     import torch
     from mbpol_openmm_plugin_b200.systems import with_virtual_sites
     g = load_golden(case)
@@ -55,7 +56,14 @@ def test_golden_fixture_device_tensors_and_m_sites(case):
     f = ctx.getForces().cpu().numpy().reshape(n, 4, 3)
     assert np.all(f[:, 3] == 0.0)
     check_case(ctx, g)
-    assert np.abs(f[:, :3].reshape(-1, 3) - (g["f2"] + g["f3"])).max() < (2e-6 if bool(g["pbc"]) else F_ATOL)
+    want = g["f2"] + g["f3"]
+    if bool(g["pbc"]):
+        from mbpol_openmm_plugin_b200.systems import particle_indices
+        idx = particle_indices(n, 4)
+        _, f2 = checker.eval_2b(pos4, idx, g["pairs"].reshape(-1, 2), g["box"], True)[:2]
+        _, f3 = checker.eval_3b(pos4, idx, g["triplets"].reshape(-1, 3), g["box"], True)[:2]
+        want = (f2 + f3).reshape(n, 4, 3)[:, :3].reshape(-1, 3)
+    assert np.abs(f[:, :3].reshape(-1, 3) - want).max() < F_ATOL
 
 
 def test_reference_test_vectors_on_gpu():
@@ -190,7 +198,14 @@ def test_synthetic_4096_against_oracle(checker):
     ctx.setPositions(torch.as_tensor(shifted.reshape(-1, 3)).cuda())
     e_s = ctx.getPotentialEnergy()
     assert abs(e_s - e) <= 1e-9 * abs(e)
-    assert np.abs(ctx.getForces().cpu().numpy() - f).max() < 2e-6
+    assert np.array_equal(ctx.getPairs(), pairs) and np.array_equal(ctx.getTriplets(), trips)
+    # forces of the translated system against the oracle evaluated on the SAME translated coordinates
+    from oracle.refbind import eval_parallel
+    e2s, f2s = eval_parallel(checker, 2, shifted.reshape(-1, 3), idx, pairs, box, True)
+    e3s, f3s = eval_parallel(checker, 3, shifted.reshape(-1, 3), idx, trips, box, True)
+    assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - e2s) <= E_RTOL * abs(e2s)
+    assert abs(ctx.energies["CalcMBPolThreeBodyForce"] - e3s) <= E_RTOL * abs(e3s)
+    assert np.abs(ctx.getForces().cpu().numpy() - (f2s + f3s)).max() < F_ATOL
 
 
 def test_owner_partition_sums_to_full():
@@ -482,10 +497,11 @@ def test_host_force_output_is_overwritten_not_accumulated():
 
 
 def test_full_size_262144_properties(checker):
-    """BASELINE config 5 (the bench workload: 262,144 waters, 4.8 M dimers, 7.1 M trimers).  The oracle cannot run the
-    whole box in test time, so: structural list invariants on the full lists, list membership AND completeness against
-    brute force for a sample of owner molecules, per-tuple energies / forces of a random tuple sample against the oracle,
-    Newton's third law and translation invariance on the full result."""
+    """BASELINE config 5 (the bench workload: 262,144 waters, 4.8 M dimers, 7.1 M trimers): structural list invariants
+    on the full lists, list membership AND completeness against brute force for a sample of owner molecules, per-tuple
+    energies / forces of a random tuple sample, and the WHOLE box -- total E2B, E3B (1e-9) and the full force array
+    (1e-6 kJ/mol/nm) -- against the oracle fanned out over the host cores (about 330 core-seconds per evaluation), on
+    the original coordinates and on a translated image of them."""
     import torch
     from mbpol_openmm_plugin_b200 import eval_tuples
     from mbpol_openmm_plugin_b200.systems import particle_indices, synthetic_box
@@ -544,6 +560,16 @@ def test_full_size_262144_properties(checker):
         _, f2 = checker.eval_2b(pos.reshape(-1, 3), idx, tp, box, True)[:2]
         _, f3 = checker.eval_3b(pos.reshape(-1, 3), idx, tt, box, True)[:2]
         assert np.abs(f[3 * m:3 * m + 3] - (f2 + f3)[3 * m:3 * m + 3]).max() < F_ATOL
+    # the whole box against the oracle: every dimer and trimer, total energies and all 786,432 x 3 force components
+    from oracle.refbind import eval_parallel
+    e2_gpu, e3_gpu = ctx.energies["CalcMBPolTwoBodyForce"], ctx.energies["CalcMBPolThreeBodyForce"]
+    e2, f2 = eval_parallel(checker, 2, pos.reshape(-1, 3), idx, pairs, box, True, chunk=40000)
+    e3, f3 = eval_parallel(checker, 3, pos.reshape(-1, 3), idx, trips, box, True, chunk=40000)
+    assert abs(e2_gpu - e2) <= E_RTOL * abs(e2) and abs(e3_gpu - e3) <= E_RTOL * abs(e3)
+    err = float(np.abs(f - (f2 + f3)).max())
+    print(f"262,144 waters, whole box vs {checker.kind} oracle: dE2/E2 = {abs(e2_gpu - e2) / abs(e2):.2e}, "
+          f"dE3/E3 = {abs(e3_gpu - e3) / abs(e3):.2e}, max |dF| = {err:.2e} kJ/mol/nm")
+    assert err < F_ATOL
     # Newton's third law over 786,432 atoms; invariance under whole-box translations of molecules
     assert np.abs(f.sum(axis=0)).max() < 1e-5
     shifted = pos.copy()
@@ -553,4 +579,13 @@ def test_full_size_262144_properties(checker):
     e_s = ctx.getPotentialEnergy()
     assert abs(e_s - e) <= 1e-9 * abs(e)
     assert np.array_equal(ctx.getPairs(), pairs)
-    assert np.abs(ctx.getForces().cpu().numpy() - f).max() < 2e-6
+    f_s = ctx.getForces().cpu().numpy()
+    # translated image: the oracle on the SAME translated coordinates for the molecules that moved the farthest, and
+    # every tuple touching them (a second whole-box oracle run would double the test time)
+    moved = np.arange(0, n, 35)[:64]                                  # shifted by both translations
+    touch2 = np.isin(pairs, moved).any(axis=1)
+    touch3 = np.isin(trips, moved).any(axis=1)
+    _, f2s = eval_parallel(checker, 2, shifted.reshape(-1, 3), idx, pairs[touch2], box, True)
+    _, f3s = eval_parallel(checker, 3, shifted.reshape(-1, 3), idx, trips[touch3], box, True)
+    rows = (3 * moved[:, None] + np.arange(3)).ravel()
+    assert np.abs(f_s[rows] - (f2s + f3s)[rows]).max() < F_ATOL

@@ -95,8 +95,11 @@ def test_gpu_onebody_with_2b_3b_device_tensors_and_wrapped_atoms(checker):
     assert abs(ctx.energies["CalcMBPolTwoBodyForce"] - g["e2"]) <= 1e-9 * abs(float(g["e2"]))
     f = ctx.getForces().cpu().numpy().reshape(n, 4, 3)
     assert np.all(f[:, 3] == 0.0)
-    want = (g["f1"] + g["f2"] + g["f3"]).reshape(n, 3, 3)
-    assert np.abs(f[:, :3] - want).max() < 2e-6
+    # the oracle on the SAME wrapped coordinates (the fixture's forces belong to the unwrapped ones)
+    _, f2 = checker.eval_2b(pos4, idx4, g["pairs"].reshape(-1, 2), box, True)[:2]
+    _, f3 = checker.eval_3b(pos4, idx4, g["triplets"].reshape(-1, 3), box, True)[:2]
+    want = (f1 + f2 + f3).reshape(n, 4, 3)[:, :3]
+    assert np.abs(f[:, :3] - want).max() < 1e-6
     # force groups: the one-body kernel alone
     ctx.forces[0].setForceGroup(3)
     assert abs(ctx.getPotentialEnergy(groups=1 << 3) - e1) <= 1e-9 * max(abs(e1), 1e-3)
