@@ -15,8 +15,13 @@ broadcast and force/energy all-reduce for N > 1].  Workload: the synthetic liqui
   roofline   the dominant kernel (pip3b_eval): algorithmic flops (111,818 per trimer) / its CUDA-event
              time inside the timed steps, against the FP64 FMA-pipe peak measured on this GPU by a register-resident
              DFMA loop (MEASURED_PEAKS.json carries no FP64 entry); nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TF
-  cpu_baseline / --impl reference : the reference's own CPU code (oracle/_ref, single thread = the Reference platform)
-             on a bounded random sample of the same workload's tuples, extrapolated by the tuple counts.
+  cpu_baseline : the reference's own CPU code (oracle/_ref), ONE thread (= the Reference platform, README.md:35), on a
+             bounded random sample of the same workload's tuples, extrapolated by the tuple counts; host CPU model and
+             core count are stated.
+  --impl reference : the same code fanned out over ALL host cores (tuple chunks on threads); a "step" is the bounded
+             sample, `ms_per_step` its measured wall time, `value` the water-steps/s the sample rate extrapolates to.
+  parity_vs_single (N > 1): before the timed region rank 0 also evaluates an UNPARTITIONED context on the same
+             positions; the run exits non-zero if the N-GPU energies / forces differ by more than 1e-9 / 1e-6.
 """
 from __future__ import annotations
 
@@ -37,6 +42,8 @@ FLOP2, FLOP3 = 30601, 111818
 # dram__bytes_read.sum + dram__bytes_write.sum of one pip3b_eval launch inside this benchmark (7,103,084 trimers):
 # profiles/r01_ncu_pip3b_eval_final_details.txt
 NCU_DRAM_BYTES_PER_TRIMER = (2.054317e9 + 2.056927e9) / 7103084
+NCU_DRAM_SOURCE = ("ncu --set full (profiles/r01_ncu_pip3b_eval_final_details.txt): 579 B per trimer (algorithmic 584 B), "
+                   "scaled by the trimers of this launch")
 NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -94,54 +101,99 @@ def make_forces(n_mol, stride=3):
     return out
 
 
-def cpu_reference_rate(pos_mol, box, n_dimers, n_trimers, seed=0):
-    """Reference code (oracle/_ref if built, else the C port) on a random sample of the workload's own tuples.
-    Returns (water-steps/s extrapolated by tuple counts, description)."""
-    from oracle.refbind import best
+def host_cpu():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1, len(os.sched_getaffinity(0))
+
+
+def cpu_reference_rate(pos_mol, box, n_dimers, n_trimers, seed=0, threads=1, lists=None):
+    """Reference code (oracle/_ref if built, else the C port) on a random sample of the workload's own tuples, on
+    `threads` host threads (1 = the Reference platform's own behaviour).
+    Returns (water-steps/s extrapolated by tuple counts, description, kind, info dict)."""
+    from oracle.refbind import best, eval_parallel
     o = best()
     posO = pos_mol[:, 0].copy()
     t0 = time.perf_counter()
-    pairs = o.pairs(posO, box, True, 0.65)
-    trips = o.triplets(posO, box, True, 0.45)
-    t_lists = time.perf_counter() - t0
+    if lists is None:
+        pairs, trips = o.pairs(posO, box, True, 0.65), o.triplets(posO, box, True, 0.45)
+        t_lists = time.perf_counter() - t0
+    else:
+        pairs, trips, t_lists = lists
     rng = np.random.default_rng(seed)
     sp = pairs[rng.choice(len(pairs), min(n_dimers, len(pairs)), replace=False)]
     st = trips[rng.choice(len(trips), min(n_trimers, len(trips)), replace=False)]
     n = len(pos_mol)
     idx = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
     pos = pos_mol.reshape(-1, 3)
+    chunk = max(500, -(-max(len(sp), len(st)) // (4 * threads)))
     t0 = time.perf_counter()
-    o.eval_2b(pos, idx, sp, box, True)
-    t2 = (time.perf_counter() - t0) / len(sp)
+    if threads == 1:
+        o.eval_2b(pos, idx, sp, box, True)
+    else:
+        eval_parallel(o, 2, pos, idx, sp, box, True, threads, chunk)
+    w2 = time.perf_counter() - t0
     t0 = time.perf_counter()
-    o.eval_3b(pos, idx, st, box, True)
-    t3 = (time.perf_counter() - t0) / len(st)
+    if threads == 1:
+        o.eval_3b(pos, idx, st, box, True)
+    else:
+        eval_parallel(o, 3, pos, idx, st, box, True, threads, chunk)
+    w3 = time.perf_counter() - t0
+    t2, t3 = w2 / len(sp), w3 / len(st)
     step_s = t_lists + len(pairs) * t2 + len(trips) * t3
-    desc = (f"{len(sp)} dimers ({t2 * 1e6:.1f} us each) + {len(st)} trimers ({t3 * 1e6:.1f} us each) drawn at random from the "
-            f"{len(pairs)} / {len(trips)} tuples of the workload, full list build {t_lists:.2f} s; extrapolated by tuple counts; "
-            f"single thread ({o.kind})")
-    return n / step_s, desc, o.kind
+    model, ncpu, avail = host_cpu()
+    desc = (f"{len(sp)} dimers ({t2 * 1e6:.2f} us each) + {len(st)} trimers ({t3 * 1e6:.2f} us each) drawn at random from the "
+            f"{len(pairs)} / {len(trips)} tuples of the workload on {threads} thread(s), full list build {t_lists:.2f} s "
+            f"(one thread); extrapolated by tuple counts; {o.kind} code; host: {model}, {ncpu} cores ({avail} usable)")
+    info = {"pairs": int(len(pairs)), "trimers": int(len(trips)), "sample_wall_s": w2 + w3, "lists_s": t_lists,
+            "full_step_s": step_s, "host_cpu": model, "host_cores": ncpu}
+    return n / step_s, desc, o.kind, info
 
 
 def run_reference_arm(args, workload, pos_mol, box):
-    """--impl reference: the reference's CPU implementation, rank 0 only."""
+    """--impl reference: the reference's CPU implementation on all host cores, rank 0 only.  One step = the full list
+    build (once, outside the steps, like a Verlet list kept for the sample) + a bounded random tuple sample; the
+    line's ms_per_step is the MEASURED wall time of a sample step, its value the water-steps/s that rate extrapolates
+    to for the whole box (tuple counts of the workload)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    rates = []
-    desc = kind = None
+    from oracle.refbind import best
+    threads = len(os.sched_getaffinity(0))
+    o = best()
+    posO = pos_mol[:, 0].copy()
+    t0 = time.perf_counter()
+    lists = (o.pairs(posO, box, True, 0.65), o.triplets(posO, box, True, 0.45))
+    lists = lists + (time.perf_counter() - t0,)
+    rows = []
+    desc = kind = info = None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r, desc, kind = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers, seed=i)
+        r, desc, kind, info = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers, seed=i, threads=threads,
+                                                 lists=lists)
         if i >= args.warmup:
-            rates.append((r, time.perf_counter() - t0))
-    value = float(np.mean([r for r, _ in rates]))
+            rows.append((r, time.perf_counter() - t0))
+    value = float(np.mean([r for r, _ in rows]))
     n = len(pos_mol)
     line = {
         "impl": "reference", "metric": "2B+3B PIP force evals/s (water-steps/s)", "value": value, "unit": "water-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n / value * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([w for _, w in rows])) * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "waters": n, "cutoff_2b_nm": 0.65, "cutoff_3b_nm": 0.45, "periodic": True},
-        "cpu_baseline": {"value": value, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc},
+        "config": {"workload": workload, "waters": n, "dimers": info["pairs"], "trimers": info["trimers"],
+                   "cutoff_2b_nm": 0.65, "cutoff_3b_nm": 0.45, "periodic": True, "lists": "rebuilt every step",
+                   "parallelism": f"host threads x{threads} over tuple chunks",
+                   "l2": "n/a (CPU)",
+                   "step": f"bounded sample: {args.ref_dimers} dimers + {args.ref_trimers} trimers per step; value = "
+                           "waters / (list build + tuples x measured time per tuple)"},
+        "full_step_ms_extrapolated": n / value * 1e3,
+        "cpu_baseline": {"value": value, "unit": "water-steps/s", "cores": threads, "kind": kind, "sample": desc,
+                         "host_cpu": info["host_cpu"], "host_cores": info["host_cores"]},
         "e2e": {"value": value, "unit": "water-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synthetic_262144")
     ap.add_argument("--ref-dimers", type=int, default=20000)
-    ap.add_argument("--ref-trimers", type=int, default=60000)
+    ap.add_argument("--ref-trimers", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -191,14 +243,13 @@ def main():
     n = len(pos_mol)
 
     if args.impl == "reference":
-        args.ref_dimers, args.ref_trimers = min(args.ref_dimers, 4000), min(args.ref_trimers, 12000)
         run_reference_arm(args, args.workload, pos_mol, box)
         return
 
     import torch
     import torch.distributed as dist
     from mbpol_openmm_plugin_b200 import MBPolContext, measure_fp64_peak
-    from mbpol_openmm_plugin_b200.distributed import CudaSliceEngine, DistributedForce
+    from mbpol_openmm_plugin_b200.distributed import NcclForce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,13 +260,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     peak_tf, _ = measure_fp64_peak()
 
-    ctx = MBPolContext(3 * n, make_forces(n), box_nm=box.tolist(), device=local, rank=rank, world=world)
+    ctx = MBPolContext(3 * n, make_forces(n), box_nm=box.tolist(), device=local)
     ctx.engine.set_timing(True)
-    dforce = DistributedForce(CudaSliceEngine(ctx), 3 * n, dev)
+    # N > 1: broadcast -> owner-partitioned evaluation -> one grouped reduce, all inside the C library (csrc/dist.cu)
+    nf = NcclForce(ctx) if world > 1 else None
     pos_dev = torch.as_tensor(pos_mol.reshape(-1, 3)).to(dev)
+    f_dev = torch.zeros(3 * n, 3, dtype=torch.float64, device=dev)
     pos_host = torch.as_tensor(pos_mol.reshape(-1, 3)).pin_memory()
     f_host = torch.zeros(3 * n, 3, dtype=torch.float64).pin_memory()
-    e_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
 
     def sync_all():
         torch.cuda.synchronize()
@@ -236,61 +289,125 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    acc = {"pip3": 0.0, "pip2": 0.0, "lists": 0.0, "b2": 0.0, "b3": 0.0, "launches": 0, "n": 0, "t3": 0, "p2": 0}
+    keys = ("ms_pip_3b", "ms_pip_2b", "ms_lists", "ms_2b", "ms_3b", "ms_reduce", "ms_bcast", "ms_comm_reduce")
+    acc = {k: 0.0 for k in keys}
+    acc.update({"launches": 0, "n": 0, "t3": 0, "p2": 0, "repartitions": 0})
 
     def step_device():
-        dforce.step(pos_dev if rank == 0 else None)
+        """one force evaluation with positions resident in HBM; energies come back to the host (16 bytes)"""
+        if world == 1:
+            f_dev.zero_()
+            energy = ctx.engine.eval_device(pos_dev, f_dev, 3, stream=stream)
+        else:
+            energy, _ = nf.step(pos_dev if rank == 0 else None)
         st = ctx.engine.stats()
-        acc["pip3"] += st["ms_pip_3b"]; acc["pip2"] += st["ms_pip_2b"]; acc["lists"] += st["ms_lists"]
-        acc["b2"] += st["ms_2b"]; acc["b3"] += st["ms_3b"]; acc["launches"] += st["n_launches"]; acc["n"] += 1
-        acc["t3"], acc["p2"] = st["n_triplets_owned"], st["n_pairs_owned"]
+        for k in keys:
+            acc[k] += st[k]
+        acc["launches"] += st["n_launches"] + (2 if world > 1 else 1)     # + broadcast and grouped reduce / + memset
+        acc["n"] += 1
+        acc["t3"], acc["p2"], acc["repartitions"] = st["n_triplets_owned"], st["n_pairs_owned"], st["n_repartitions"]
+        return energy
 
     def step_e2e():
+        """the same through the public API with HOST buffers: pinned positions in, forces + energies out, every step"""
         if world == 1:
-            # public API with host arrays: C-ABI mbpol_eval_host copies positions in and forces / energies out
             ctx.setPositions(pos_host.numpy())
             ctx.setForceOutput(f_host.numpy())
             ctx.calcForcesAndEnergy()
         else:
-            energy, force = dforce.step(pos_host if rank == 0 else None)      # pinned host -> device -> broadcast
+            _, force = nf.step(pos_host if rank == 0 else None)              # pinned host -> device -> broadcast
             if rank == 0:
                 f_host.copy_(force, non_blocking=True)
-                e_host.copy_(energy, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+
+    # ---- parity of the N-GPU path against ONE unpartitioned context on the same positions (rank 0), before timing
+    parity = None
+    totals = None
+    if world > 1:
+        energy = step_device()
+        if rank == 0:
+            one = MBPolContext(3 * n, make_forces(n), box_nm=box.tolist(), device=local)
+            f1 = torch.zeros_like(f_dev)
+            e1 = one.engine.eval_device(pos_dev, f1, 3, stream=stream)
+            st1 = one.engine.stats()
+            totals = (int(st1["n_pairs"]), int(st1["n_triplets"]))
+            parity = {"rel_dE2": abs(energy[0] - e1[0]) / abs(e1[0]), "rel_dE3": abs(energy[1] - e1[1]) / abs(e1[1]),
+                      "max_abs_dF": float((nf.force - f1).abs().max().item()),
+                      "bars": {"rel_dE": 1e-9, "max_abs_dF_kJ_mol_nm": 1e-6},
+                      "against": "one unpartitioned context, same positions, same GPU as rank 0"}
+            parity["ok"] = bool(parity["rel_dE2"] <= 1e-9 and parity["rel_dE3"] <= 1e-9 and parity["max_abs_dF"] <= 1e-6)
+            del f1
+            one.engine.close()
+        ok = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
+        dist.broadcast(ok, src=0)
+        if not int(ok.item()):
+            if rank == 0:
+                _emit({"error": "N-GPU result differs from the single-GPU result", "parity_vs_single": parity,
+                       "n_gpus": world})
+            dist.destroy_process_group()
+            sys.exit(3)
 
     for _ in range(args.warmup):
         step_device()
     for k in acc:
         acc[k] = 0 if isinstance(acc[k], int) else 0.0
+    rep0 = ctx.engine.stats()["n_repartitions"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     stats = ctx.engine.stats()
+    rep_in_window = stats["n_repartitions"] - rep0
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # ---- the rebalancing step (full list build on every rank) happens every MBPOL_REPARTITION_EVERY = 50 evaluations:
+    # time single steps until one contains it, so that its cost is on record next to the steady-state number
+    repart = None
+    if world > 1:
+        every = int(os.environ.get("MBPOL_REPARTITION_EVERY", "50"))
+        slow = None
+        for _ in range(every + 2 if every > 0 else 0):
+            before = ctx.engine.stats()["n_repartitions"]
+            t = timed(step_device, 1)
+            if ctx.engine.stats()["n_repartitions"] != before:
+                slow = t
+                break
+        repart = {"every_evaluations": every, "steps_with_rebalance_in_timed_window": int(rep_in_window),
+                  "ms_of_a_step_with_rebalance": slow,
+                  "amortised_ms_per_step": (ms / args.steps) + ((slow - ms / args.steps) / every if slow and every else 0.0)}
+
     if rank == 0:
-        n_pairs, n_trips = stats["n_pairs"], stats["n_triplets"]
+        n_pairs, n_trips = totals if totals else (int(stats["n_pairs"]), int(stats["n_triplets"]))
         value = n * args.steps / (ms * 1e-3)
         e2e = n * args.steps / (ms_e2e * 1e-3)
         k = max(acc["n"], 1)
-        ms_pip3 = acc["pip3"] / k
+        ms_pip3 = acc["ms_pip_3b"] / k
         achieved = acc["t3"] * FLOP3 / (ms_pip3 * 1e-3) / 1e12 if ms_pip3 > 0 else 0.0
-        ms_pip2 = acc["pip2"] / k
+        ms_pip2 = acc["ms_pip_2b"] / k
         ach2 = acc["p2"] * FLOP2 / (ms_pip2 * 1e-3) / 1e12 if ms_pip2 > 0 else 0.0
+        both = (acc["p2"] * FLOP2 + acc["t3"] * FLOP3) / ((ms_pip2 + ms_pip3) * 1e-3) / 1e12 if ms_pip2 + ms_pip3 > 0 else 0.0
         from mbpol_openmm_plugin_b200 import _lib
         ni3 = _lib.load().mbpol_pip_instruction_count(3)
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        step_ms = ms / args.steps
+        stage = {"lists": acc["ms_lists"] / k, "2b": acc["ms_2b"] / k, "3b": acc["ms_3b"] / k,
+                 "force_scatter": acc["ms_reduce"] / k, "pip2b_eval": ms_pip2, "pip3b_eval": ms_pip3,
+                 "tuple_stage_2b_without_pip": acc["ms_2b"] / k - ms_pip2, "tuple_stage_3b_without_pip": acc["ms_3b"] / k - ms_pip3}
+        if world > 1:
+            stage.update({"broadcast": acc["ms_bcast"] / k, "reduce": acc["ms_comm_reduce"] / k})
+        stage["rest"] = step_ms - sum(stage[x] for x in ("lists", "2b", "3b"))
+        model, ncpu, _ = host_cpu()
         line = {
             "metric": "2B+3B PIP force evals/s (water-steps/s)", "value": value, "unit": "water-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "waters": n, "dimers": int(n_pairs), "trimers": int(n_trips),
                        "cutoff_2b_nm": 0.65, "cutoff_3b_nm": 0.45, "periodic": True, "lists": "rebuilt every step",
-                       "parallelism": f"owner-molecule partition x{world}",
+                       "parallelism": f"owner-molecule partition x{world}" +
+                                      (", NCCL broadcast + grouped reduce inside libmbpol_b200.so" if world > 1 else ""),
                        "l2": "per-step working set (variables, gradients, force blocks: several GB) exceeds the 126 MB L2"},
             "alg_tflops": (n_pairs * FLOP2 + n_trips * FLOP3) * args.steps / (ms * 1e-3) / 1e12,
             "frac_of_nominal_fp64_peak": (n_pairs * FLOP2 + n_trips * FLOP3) * args.steps / (ms * 1e-3) / 1e12
@@ -299,29 +416,36 @@ def main():
                     "h2d_bytes_per_step": int(pos_host.numel() * 8),
                     "d2h_bytes_per_step": int(f_host.numel() * 8 + 16)},
             "gpu_launches": int(acc["launches"]),
-            "stage_ms": {"lists": acc["lists"] / k, "2b": acc["b2"] / k, "3b": acc["b3"] / k, "pip2b_eval": ms_pip2,
-                         "pip3b_eval": ms_pip3},
+            "stage_ms": stage,
             "roofline": {"bound": "fp64", "kernel": "pip3b_eval", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                         # dram__bytes_read+write of one `ncu --set full` capture of this kernel (profiles/
-                         # r01_ncu_pip3b_eval_final_details.txt: 4.11 GB for 7,103,084 trimers) scaled to this launch
+                         # dram__bytes_read+write of one `ncu --set full` capture of this kernel scaled to this launch
                          "traffic": acc["t3"] * NCU_DRAM_BYTES_PER_TRIMER, "traffic_unit": "bytes per launch",
-                         "traffic_source": "ncu --set full, 579 B per trimer (algorithmic 584 B), scaled by trimers per launch",
+                         "traffic_source": NCU_DRAM_SOURCE,
                          "peak_source": "measured on this GPU: register-resident DFMA loop (mbpol_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": NOMINAL_FP64_TF, "frac_of_nominal": achieved / NOMINAL_FP64_TF,
                          "fp64_instr_per_trimer": ni3,
                          "fp64_pipe_issue_util": acc["t3"] / 32 * ni3 / (ms_pip3 * 1e-3) / (148 * 2 * sm_hz) if ms_pip3 > 0 else None,
-                         "share_of_step": ms_pip3 / (ms / args.steps), "pip2b_eval_tflops": ach2,
+                         "share_of_step": ms_pip3 / step_ms, "pip2b_eval_tflops": ach2,
+                         "pip2b_frac": ach2 / peak_tf if peak_tf else None,
+                         "pip2b_plus_pip3b_tflops": both, "pip2b_plus_pip3b_frac": both / peak_tf if peak_tf else None,
                          "algorithmic_flops_per_launch": acc["t3"] * FLOP3},
             "clocks": clocks,
+            "host": {"cpu": model, "cores": ncpu},
         }
+        if parity is not None:
+            line["parity_vs_single"] = parity
+        if repart is not None:
+            line["repartition"] = repart
         if world == 1 and not args.no_cpu_baseline:
-            v, desc, kind = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers)
-            line["cpu_baseline"] = {"value": v, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc}
+            v, desc, kind, info = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers)
+            line["cpu_baseline"] = {"value": v, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc,
+                                    "host_cpu": info["host_cpu"], "host_cores": info["host_cores"]}
         _emit(line)
     if world > 1:
         dist.barrier()
+        nf.close()
         dist.destroy_process_group()
 
 

@@ -41,48 +41,46 @@ def test_table_reproduces_reference_polynomial_values(name):
         assert np.abs(G - grad).max() <= 1e-12 * np.abs(grad).max()
 
 
-@pytest.mark.parametrize("name,n_classes,opts", [
-    ("pip2b", 1, {}), ("pip3b", 1, {}), ("pip2b", 2, {}), ("pip3b", 2, {}), ("pip3b", 3, {}),
-    ("pip3b", 1, {"npair": 8}), ("pip2b", 1, {"nstatic": 32}), ("pip3b", 1, {"nstatic": 48}),
-    # symmetry phases (the shipped configuration: mbpol_openmm_plugin_b200/build.py GEN_ARGS) and their options
-    ("pip2b", 1, {"sym": 12, "sib": True, "fall": 4, "npre": 4, "piece": 32, "block": 384}),
-    ("pip3b", 1, {"sym": 32, "sib": True, "fall": 4, "npre": 8, "piece": 64}),
-    ("pip2b", 1, {"sym": 16, "skeleton_weight": 0}), ("pip3b", 1, {"sym": 24, "skeleton_weight": 0})])
-def test_command_stream_matches_table(name, n_classes, opts, tmp_path):
-    """python interpreter of the packed streams (the same records the GPU kernels execute) vs the monomial definition;
-    with several variable classes the partial values and gradients of the class streams must add up."""
-    meta, streams = gen_interp.generate(name, str(tmp_path), n_classes=n_classes, **opts)
-    assert len(streams) == n_classes == len(meta["kernels"])
+@pytest.mark.parametrize("name,opts", [
+    # the shipped configurations (mbpol_openmm_plugin_b200/build.py GEN_ARGS) and neighbouring settings
+    ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384}),
+    ("pip3b", {"sym": 32, "npre": 8, "piece": 64}),
+    ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 16}),
+    ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 13}),
+    ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 32, "group": 2}),
+    ("pip2b", {"sym": 16, "skeleton_weight": 0}), ("pip3b", {"sym": 24, "skeleton_weight": 0, "fall": 0})])
+def test_command_stream_matches_table(name, opts, tmp_path):
+    """python interpreter of the packed stream (the same records the GPU kernel executes) vs the monomial definition"""
+    meta, words, masks, phases, dual = gen_interp.generate(name, str(tmp_path), **opts)
     t = dict(np.load(os.path.join(DATA, name + ".npz")))
     rng = np.random.default_rng(11)
     for _ in range(2):
         x = rng.uniform(0.05, 1.6, int(t["n_vars"]))
-        E, G = 0.0, 0.0
-        for words, masks, combos in streams:
-            e, g = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, combos, meta.get("phases"))
-            E, G = E + e, G + g
+        E, G = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, phases, dual)
         Er, Gr = extract_pip.eval_table(t, x)
         assert abs(E - Er) <= 1e-13 * max(1.0, abs(Er))
         assert np.abs(G - Gr).max() <= 1e-13 * np.abs(Gr).max()
     # stream layout invariants the kernel relies on
     cw = meta["chunk_bytes"] // 8
-    for words, _, _ in streams:
-        assert len(words) % cw == 0 and not words[-cw:].any()           # trailing all-zero look-ahead chunk
+    assert len(words) % cw == 0 and not words[-cw:].any()           # trailing all-zero look-ahead chunk
     assert meta["smem_bytes"] <= 227 * 1024
-    if opts.get("sym"):
-        # every variable belongs to exactly one orbit of every phase; phase 0 is the identity
-        nv = int(t["n_vars"])
-        assert meta["phases"][0] == [[j] for j in range(nv)]
-        for orbs in meta["phases"]:
-            assert sorted(v for o in orbs for v in o) == list(range(nv))
-        assert meta["fp64_instr"] < {"pip2b": 24000, "pip3b": 67000}[name]     # vs 30,180 / 79,182 without symmetry
+    # every variable belongs to exactly one orbit of every phase; phase 0 is the identity
+    nv = int(t["n_vars"])
+    assert meta["phases"][0] == [[j] for j in range(nv)]
+    for orbs in meta["phases"]:
+        assert sorted(v for o in orbs for v in o) == list(range(nv))
+    assert meta["fp64_instr"] < {"pip2b": 24000, "pip3b": 67000}[name]     # vs 30,180 / 79,182 without symmetry
+    if opts.get("dual_max"):
+        assert meta["records"]["dual"] > 0.3 * (meta["records"]["dual"] + meta["records"].get("leafnode", 0))
 
 
-def test_shipped_generator_settings_are_the_tested_ones():
+def test_shipped_generator_settings_are_tested():
+    """whatever build.py ships must be one of the configurations test_command_stream_matches_table interprets"""
     from mbpol_openmm_plugin_b200 import build
     a = build.GEN_ARGS
-    assert (a["sym2"], a["sym3"], a["sib"], a["fall"], a["npre"], a["piece"]) == (12, 32, True, 4, 8, 64)
+    assert (a["sym2"], a["sym"], a["npre"], a["piece"], a["block"]) == (12, 32, 8, 64, 256)
     assert (a["block2"], a["piece2"], a["npre2"]) == (384, 32, 4)
+    assert a["dual"] in (0, 13, 32) and a["dual2"] in (0, 16)
 
 
 @pytest.mark.parametrize("name", ["pip2b", "pip3b"])

@@ -1,63 +1,86 @@
-"""Code generator v2: monomial table -> *cache-resident* adjoint-Horner evaluator (command stream + small PTX kernel).
+"""Code generator: monomial table -> cache-resident adjoint-Horner evaluator (command stream + small sm_100a PTX kernel).
 
-Measured on B200 (profiles/r01_*): the fully unrolled adjoint-Horner program of tools/gen_horner.py (27 k / 72 k FP64
-instructions, 0.4 / 1.4 MB of SASS) is instruction-fetch bound -- 38 % of warp stall cycles are `no_instruction`, FP64
-pipe 31 % (3B) / 49 % (2B); a loop body of <= ~1.2 k instructions runs the same instruction mix at 84 %.  So the program
-is turned into DATA: the Horner tree is serialised depth-first into a command stream (global memory, read by every warp
-at the same address -> one L1/L2-resident sector per request) and a ~1 k-instruction kernel interprets it with all
-per-tuple state in registers:
+The polynomial E(x) = sum_m a[c_m] prod_{v in m} x_v (data/pip{2b,3b}.npz, degree <= 4) is factored as a greedy
+multivariate Horner tree and value + reverse-mode gradient are computed in ONE depth-first pass:
 
-    ENTER_d k, c0 : push (v, a);  a *= x_k;  v = c0                      (x_k: dynamic index -> shared-memory copy of x)
-    MASK_m coefs  : for every variable j of the blocks in mask m:  v += c_j x_j ;  g_j += c_j a     (static registers)
-    LEAVE_d k     : w = v; pop (v, a);  v += x_k w ;  g_k += a w         (g_k: dynamic -> shared-memory accumulator)
+    node(M, adj):  v = const(M)
+       leaf  a_k x_i :  v = fma(a_k, x_i, v)      g_i = fma(a_k, adj, g_i)
+       inner x_i (..):  w = node(M / x_i, adj x_i)  v = fma(x_i, w, v)   g_i = fma(adj, w, g_i)
 
-Leaves of a node are stored *densely* per symmetry block of variables (zero coefficients where a monomial is absent):
-the leaves cluster by block, so the padding costs only 11 % extra FMAs while the MASK handlers need no indexing at all.
-Only 32 (3B) / 19 (2B) distinct (block-mask) patterns occur.
+Fully unrolled this is 1.4 MB of SASS and instruction-fetch bound (profiles/r01_*; tools/attic/gen_horner_r01.py), so
+the program is DATA: the tree is serialised depth-first into a command stream and a few-thousand-instruction kernel
+interprets it, one thread per tuple, all per-tuple state in registers:
 
-FP64 instructions per tuple: 2 * dense slots + 4 per node = ~79 k (3B), ~30 k (2B).
+    ENTER_d k, c0  : push (v, a);  a *= x_k;  v = c0               (x_k: dynamic index -> shared-memory copy of x)
+    LEAVE_d k      : w = v; pop (v, a);  v += x_k w;  g_k += a w   (g_k: dynamic -> shared-memory accumulator)
+    SIBLING_d      : LEAVE_d k_old + ENTER_d k_new, c0 in one record
+    MASK_h coefs   : for every register slot j of handler h:  v += c_j x_j ;  g_j += c_j a
+    LEAFNODE_h     : ENTER + MASK_h + LEAVE fused (nodes without inner children: 83 % of all nodes)
+    DUAL_h         : two consecutive LEAFNODE_h records (siblings) in one dispatch, coefficients interleaved
+    TRANSITION_p   : end of symmetry phase p (see below)
+    NEXT / END     : flip the stream buffers / finish
 
-Shipped configuration (mbpol_openmm_plugin_b200/build.py GEN_ARGS), all measured on B200:
+Symmetry phases.  Every variable is a function of ONE site-site distance; a hydrogen (or lone-pair)
+swap inside one molecule permutes the variables and leaves the polynomial invariant.  A node whose leaf coefficients
+are invariant under a set S of swaps is a linear form in the S-ORBIT SUMS of the variables, and its gradient
+contribution is the same number for every member of an orbit.  The stream is run in PHASES, one per subgroup S that
+pays for itself: the registers hold the orbit sums of that phase (slot = lowest variable of the orbit), the leaf
+handlers work on slots, TRANSITION scatters the register gradients to the orbit members and loads the next phase.
+Leaf handlers are specialised on register-slot SETS chosen by an agglomerative merge (`merge_library`); payloads are
+dense per handler (zero padding), so a handler needs no indexing at all.
 
-  * symmetry phases (`serialise_sym`): hydrogen / lone-pair swaps permute the variables; a node whose leaf coefficients are
-    invariant under a set of swaps is evaluated on the ORBIT SUMS of the variables, in a phase of the stream in which the
-    registers hold those sums -> 64 k (3B) / 22 k (2B) FP64 instructions; leaf handlers are specialised on arbitrary
-    register-slot sets chosen by an agglomerative merge (`merge_library`) instead of on symmetry blocks;
-  * SIBLING_d records (LEAVE_d + ENTER_d in one dispatch), look-ahead opcodes (LOOKAHEAD: the dispatch stays in the
-    uniform datapath, BRXU), a second copy of the leaf handlers that follow themselves (`fall`);
-  * the stream is staged in 16 KB chunks with cp.async straight into the idle shared-memory buffer (`piece` > 16);
-  * the 2B kernel runs 384 threads per CTA (168 registers -> 3 warps per scheduler).
+DUAL records (round 2).  90 % (3B) / 95 % (2B) of the leaf-node records sit next to a sibling with the same handler.
+One handler evaluates both: four independent value chains instead of two (the dependent-issue stalls of the value FMAs
+were the largest stall reason of the round-1 kernel), the second value FMA of a slot reads x_j from the operand-reuse
+cache (a DFMA with three fresh 64-bit register operands issues every third cycle, not every second,
+profiles/r01_dfma_operand_microbench.md), and header / dispatch / address arithmetic are paid once per two records.
 
-Everything else in this file (class split, PAIR / STATIC handlers, constant-bank stream, x_k prefetch, separate tail,
-...) is an experiment that was built, verified and timed, and lost (profiles/r01_microbench_*.log).
+The round-1 experiments that lost (variable-class kernels, STATIC handlers, constant-bank stream, x_k prefetch, ...)
+live in tools/attic/gen_interp_r01.py together with their measurements' pointers; this file is the shipped path plus
+the knobs that are still being measured.
 """
 from __future__ import annotations
 
 import argparse
 import collections
+import itertools
 import json
 import os
 import struct
 
 import numpy as np
 
-from gen_horner import DATA, GEN, PAD, split_greedy
+PAD = 255
+HERE = os.path.dirname(os.path.abspath(__file__))
+DATA = os.path.join(HERE, "..", "mbpol_openmm_plugin_b200", "data")
+GEN = os.path.join(HERE, "..", "mbpol_openmm_plugin_b200", "csrc", "gen")
 
-# variable blocks = orbits of the variables under the permutation group, split by molecule role
-BLOCKS = {
-    "pip3b": [[0, 1, 2], [3, 4, 5, 6, 7, 8], [9, 10, 11, 12], [13, 14, 15, 16], [17, 18, 19, 20], [21, 22, 23, 24],
-              [25, 26, 27, 28], [29, 30, 31, 32], [33, 34, 35]],
-    "pip2b": [[0, 1], [2, 3, 4, 5], [6, 7, 8, 9], [10, 11, 12, 13], [14], [15, 16, 17, 18], [19, 20, 21, 22], [23, 24],
-              [25, 26], [27, 28, 29, 30]],
-}
-OP_END, OP_ENTER, OP_LEAVE, OP_NEXT, OP_MASK = 0, 1, 4, 7, 8   # ENTER_d = 1..3, LEAVE_d = 4..6, MASK_m = 8 + m,
-# LEAFNODE_m = 8 + n_masks + m  (ENTER + MASK_m + LEAVE fused for nodes without children: 83 % of all nodes)
+NV = {"pip2b": 31, "pip3b": 36}
+OP_END, OP_ENTER, OP_LEAVE, OP_NEXT, OP_MASK = 0, 1, 4, 7, 8
+# ENTER_d = 1..3, LEAVE_d = 4..6, MASK_h = 8 + h, LEAFNODE_h = 8 + nm + h, TRANSITION_p = 8 + 2 nm + p,
+# SIBLING_d = 8 + 2 nm + n_phases + d - 1, DUAL_i = 8 + 2 nm + n_phases + 3 + i (i indexes the handlers that have one)
 MAX_DEPTH = 3
-# Header layout.  LOOKAHEAD: the low word of record r's header holds the opcode of record r + 1 (word 0 of the stream
-# holds the first opcode), so a handler knows its successor on entry and the jump-table read + address arithmetic of
-# its closing brx.idx no longer wait for the shared-memory load of the next header (ncu: 8 % of the warp stall cycles
-# were short-scoreboard stalls of exactly that chain).
-LOOKAHEAD = bool(int(os.environ.get("PIP_LOOKAHEAD", "1")))
+
+
+def split_greedy(monos):
+    """Yield (var, sub-monomials) groups: repeatedly pull out the variable that divides most remaining monomials."""
+    rest = monos
+    while rest:
+        cnt = collections.Counter()
+        for vs, _ in rest:
+            for v in set(vs):
+                cnt[v] += 1
+        best = max(cnt.items(), key=lambda kv: (kv[1], -kv[0]))[0]
+        sub, other = [], []
+        for vs, a in rest:
+            if best in vs:
+                lst = list(vs)
+                lst.remove(best)
+                sub.append((tuple(lst), a))
+            else:
+                other.append((vs, a))
+        rest = other
+        yield best, sub
 
 
 class Node:
@@ -84,134 +107,10 @@ def build_tree(monos, var=None):
     return node
 
 
-def static_combos(recs, nm, nstatic):
-    """the `nstatic` most frequent (mask id, node variable) pairs among the fused leaf-node records"""
-    freq = collections.Counter((op - OP_MASK - nm, k) for op, k, _ in recs if OP_MASK + nm <= op < OP_MASK + 2 * nm)
-    return [c for c, _ in freq.most_common(nstatic)]
-
-
-def serialise(name, tab, fuse=True, class_blocks=None, with_consts=True, npair=0, nstatic=0):
-    """-> (records, masks).  records: list of (opcode, k, payload doubles); masks: list of block-index tuples.
-
-    ``class_blocks`` restricts the program to the leaves whose variable lies in those blocks (the polynomial is linear in
-    its leaf sums, so the classes' partial values and gradients simply add); ``with_consts`` says whether this class
-    also carries the monomials that end at an inner node."""
-    blocks = BLOCKS[name]
-    use = list(range(len(blocks))) if class_blocks is None else list(class_blocks)
-    cvars = set(v for b in use for v in blocks[b])
-    coef = tab["coef"]
-    monos = [(tuple(int(v) for v in row if v != PAD), int(c)) for row, c in zip(tab["mono_vars"], tab["mono_coef"])]
-    root = build_tree(monos)
-    freq = collections.Counter()
-    keep = {}
-
-    def has(node):
-        r = keep.get(id(node))
-        if r is None:
-            r = any(v in cvars for v in node.leaves) or (with_consts and node.const is not None)
-            for k in node.kids:
-                r = has(k) or r
-            keep[id(node)] = r
-        return r
-
-    def leaves_of(node):
-        return {v: c for v, c in node.leaves.items() if v in cvars}
-
-    def mask_of(node):
-        return tuple(b for b in use if any(v in node.leaves for v in blocks[b]))
-
-    def count(node):
-        if leaves_of(node):
-            freq[mask_of(node)] += 1
-        for k in node.kids:
-            if has(k):
-                count(k)
-    has(root)
-    count(root)
-    masks = [m for m, _ in freq.most_common()]
-    mask_id = {m: i for i, m in enumerate(masks)}
-    recs = []
-
-    def const_of(node):
-        return coef[node.const] if (with_consts and node.const is not None) else 0.0
-
-    def emit(node, depth):
-        assert depth <= MAX_DEPTH
-        lv = leaves_of(node)
-        kids = [k for k in node.kids if has(k)]
-        # evaluation order of siblings is free: group the childless ones by mask so that equal records are adjacent
-        def order(k):
-            childless = not any(has(q) for q in k.kids) and bool(leaves_of(k))
-            return (0, mask_id[mask_of(k)]) if childless else (1, 0)
-        kids.sort(key=order)
-        if depth > 0 and not kids and lv and fuse:
-            m = mask_of(node)
-            payload = [const_of(node)] + [coef[lv[v]] if v in lv else 0.0 for b in m for v in blocks[b]]
-            recs.append((OP_MASK + len(masks) + mask_id[m], node.var, payload))
-            return
-        if depth > 0:
-            recs.append((OP_ENTER + depth - 1, node.var, [const_of(node)]))
-        else:
-            assert node.const is None
-        if lv:
-            m = mask_of(node)
-            payload = [coef[lv[v]] if v in lv else 0.0 for b in m for v in blocks[b]]
-            recs.append((OP_MASK + mask_id[m], 0, payload))
-        for k in kids:
-            emit(k, depth + 1)
-        if depth > 0:
-            recs.append((OP_LEAVE + depth - 1, node.var, []))
-    emit(root, 0)
-    recs.append((OP_END, 0, []))
-    if nstatic:
-        # STATIC_c = LEAFNODE_m whose node variable k is fixed by the opcode: x_k and g_k are plain registers in the
-        # handler, the shared-memory read of x_k and the read-modify-write of g_k disappear
-        nm = len(masks)
-        combos = static_combos(recs, nm, nstatic)
-        cid = {c: i for i, c in enumerate(combos)}
-        recs = [(OP_MASK + 3 * nm + cid[(op - OP_MASK - nm, k)], k, pl)
-                if (OP_MASK + nm <= op < OP_MASK + 2 * nm and (op - OP_MASK - nm, k) in cid) else (op, k, pl)
-                for op, k, pl in recs]
-        serialise.combos[name] = combos
-    if npair:
-        # PAIR_m = two consecutive LEAFNODE_m records evaluated by one handler with interleaved, independent chains
-        pairable = pair_masks(name, masks, npair)
-        nm, merged, i = len(masks), [], 0
-        while i < len(recs):
-            op, k, pl = recs[i]
-            m = op - OP_MASK - nm
-            if m in pairable and i + 1 < len(recs) and recs[i + 1][0] == op:
-                merged.append((OP_MASK + 2 * nm + pairable.index(m), k | (recs[i + 1][1] << 8),
-                               list(pl) + list(recs[i + 1][2])))
-                i += 2
-            else:
-                merged.append(recs[i])
-                i += 1
-        recs = merged
-    return recs, masks
-
-
-def pair_masks(name, masks, npair, max_slots=18):
-    """mask ids (most frequent first) that get a PAIR handler: small enough that two payloads fit the register budget"""
-    blocks = BLOCKS[name]
-    ok = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= max_slots]
-    return ok[:npair]
-
-
-serialise.combos = {}
-
-
-
-# ---- symmetry phases ------------------------------------------------------------------------------------------------
-# Each variable is a function of ONE site-site distance (SURVEY.md App. A); a hydrogen (or lone-pair) swap inside one
-# molecule permutes the variables and leaves the polynomial invariant.  A Horner node whose leaf coefficients are
-# invariant under a set S of swaps is a linear form in the S-ORBIT SUMS of the variables:  sum_i c_i x_i =
-# sum_orbits c_O (sum_{i in O} x_i), and its gradient contribution is the same number for every member of an orbit.
-# The program is therefore run in PHASES, one per subgroup S that occurs: at the start of a phase the registers are
-# loaded with the orbit sums (slot = lowest variable of the orbit), the leaf handlers work on those slots only, and at
-# the end of the phase the register gradients are scattered to all orbit members.  ENTER / LEAVE keep using the
-# original variables (shared-memory copies), so the tree skeleton is the same in every phase.
+# ---- symmetry -----------------------------------------------------------------------------------------------------------
 def _sites(name):
+    """site pair of every variable (the same table as MBPOL_{2B,3B}_VARS in csrc/tuples.cu) and the
+    site swaps that leave the polynomial invariant"""
     if name == "pip3b":
         p = [("Ha1", "Ha2"), ("Hb1", "Hb2"), ("Hc1", "Hc2"), ("Oa", "Ha1"), ("Oa", "Ha2"), ("Ob", "Hb1"), ("Ob", "Hb2"),
              ("Oc", "Hc1"), ("Oc", "Hc2")]
@@ -283,11 +182,9 @@ def merge_library(req, K):
     return sets
 
 
-def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
-    """-> (records, masks, phases).  masks: handler slot tuples; phases: list of orbit lists (phase 0 = identity).
-    Opcodes: MASK_h = OP_MASK + h, LEAFNODE_h = OP_MASK + nm + h, TRANSITION_p = OP_MASK + 2 nm + p (scatter the
-    register gradients of phase p, load the orbit sums of phase p + 1)."""
-    import itertools
+def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
+    """-> (records, masks, phases, dual).  records: (opcode, k, payload doubles); masks: handler slot tuples; phases: list
+    of orbit lists (phase 0 = identity); dual: handler ids that have a DUAL record type, in opcode order."""
     nv = int(tab["n_vars"])
     coef = tab["coef"]
     monos = [(tuple(int(v) for v in row if v != PAD), int(c)) for row, c in zip(tab["mono_vars"], tab["mono_coef"])]
@@ -342,7 +239,7 @@ def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
     used = sorted(allowed, key=lambda S: (len(S), S))
     pidx = {S: i for i, S in enumerate(used)}
     phases = [orbs[S] for S in used]
-    bits = lambda need: sum(1 << j for j in need)
+    bits = lambda need: sum(1 << j for j in need)  # noqa: E731
     req = collections.Counter(bits(need) for _, need in cls.values())
     lib = merge_library(req, K)
     fr = collections.Counter()
@@ -379,7 +276,7 @@ def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
         const = coef[node.const] if (node.const is not None and p == min(leafph[id(node)])) else 0.0
         h = hid[pick[bits(cls[id(node)][1])]] if own else -1
 
-        def order(k):
+        def order(k):       # evaluation order of siblings is free: childless ones grouped by handler -> equal records adjacent
             childless = not any(p in leafph[id(q)] for q in k.kids)
             return (0, hid[pick[bits(cls[id(k)][1])]]) if childless else (1, 0)
         kids.sort(key=order)
@@ -402,19 +299,35 @@ def serialise_sym(name, tab, K, skeleton_weight=40, sib=False):
             emit(root, 0, p)
         recs.append((OP_MASK + 2 * nm + p, 0, []))
     recs.append((OP_END, 0, []))
-    if sib:
-        # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record, one dispatch (k = k_new | k_old << 8)
-        base, out, i = OP_MASK + 2 * nm + len(phases), [], 0
+    # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record (k = k_new | k_old << 8)
+    base, out, i = OP_MASK + 2 * nm + len(phases), [], 0
+    while i < len(recs):
+        op, k, pl = recs[i]
+        if OP_LEAVE <= op < OP_NEXT and i + 1 < len(recs) and recs[i + 1][0] == op - OP_LEAVE + OP_ENTER:
+            out.append((base + op - OP_LEAVE, recs[i + 1][1] | (k << 8), recs[i + 1][2]))
+            i += 2
+        else:
+            out.append(recs[i])
+            i += 1
+    recs = out
+    # DUAL_i = two consecutive LEAFNODE_h records (always siblings: distinct node variables), for handlers of at most
+    # dual_max slots: k = k_A | k_B << 8, payload = c0_A, c0_B, c_A1, c_B1, c_A2, c_B2, ... (interleaved)
+    dual = [h for h in range(nm) if len(masks[h]) <= dual_max]
+    if dual:
+        dbase, out, i = base + MAX_DEPTH, [], 0
         while i < len(recs):
             op, k, pl = recs[i]
-            if OP_LEAVE <= op < OP_NEXT and i + 1 < len(recs) and recs[i + 1][0] == op - OP_LEAVE + OP_ENTER:
-                out.append((base + op - OP_LEAVE, recs[i + 1][1] | (k << 8), recs[i + 1][2]))
+            h = op - OP_MASK - nm
+            if 0 <= h < nm and h in dual and i + 1 < len(recs) and recs[i + 1][0] == op:
+                kb, plb = recs[i + 1][1], recs[i + 1][2]
+                assert kb != k and len(pl) == len(plb)
+                out.append((dbase + dual.index(h), k | (kb << 8), [c for ab in zip(pl, plb) for c in ab]))
                 i += 2
             else:
                 out.append(recs[i])
                 i += 1
         recs = out
-    return recs, masks, phases
+    return recs, masks, phases, dual
 
 
 def rec_words(n_payload):
@@ -425,8 +338,9 @@ def pack(recs, chunk_bytes):
     """u64 words, organised in chunks of ``chunk_bytes`` that the kernel stages through shared memory one at a time.
     Inside a chunk, word 0 is padding so that every record header sits at byte offset 8 (mod 16) and every payload is
     16-byte aligned (payloads are padded to an odd number of words).  No record straddles a chunk: the last record of a
-    chunk is OP_NEXT.  One all-zero chunk is appended so that the kernel's look-ahead load never leaves the array.
-    With LOOKAHEAD the opcode stored in a header is the NEXT record's (see above)."""
+    chunk is OP_NEXT.  One all-zero chunk is appended so that the kernel's look-ahead loads never leave the array.
+    Look-ahead opcodes: the low word of record r's header holds the opcode of record r + 1 (word 0 of the stream holds
+    the first opcode), so a handler knows its successor on entry and its closing brx.idx never waits for a load."""
     cw = chunk_bytes // 8
     chunks = []
     cur = [0]
@@ -448,25 +362,25 @@ def pack(recs, chunk_bytes):
     cur += [0] * (cw - len(cur))
     chunks.append(cur)
     chunks.append([0] * cw)
-    if LOOKAHEAD:
-        chunks[0][0] = hdrs[0][2]
-        for (c, i, _), (_, _, nxt) in zip(hdrs, hdrs[1:] + [(0, 0, OP_END)]):
-            chunks[c][i] = (chunks[c][i] & ~0xFFFFFFFF) | nxt
+    chunks[0][0] = hdrs[0][2]
+    for (c, i, _), (_, _, nxt) in zip(hdrs, hdrs[1:] + [(0, 0, OP_END)]):
+        chunks[c][i] = (chunks[c][i] & ~0xFFFFFFFF) | nxt
     return np.array([w for c in chunks for w in c], dtype=np.uint64)
 
 
-def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
-    """numpy/python reference interpreter of the packed stream (used by the CPU tests).  With ``phases`` (symmetry
-    mode) the handlers work on register slots xr / gr that hold orbit sums, ENTER / LEAVE on the original variables."""
+def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
+    """numpy/python reference interpreter of the packed stream (used by the CPU tests): the same records, in the same
+    order, with the same meaning as the PTX handlers below."""
     cw = chunk_bytes // 8
-    nv = sum(len(b) for b in BLOCKS[name])
-    blocks = [[j] for j in range(nv)] if phases else BLOCKS[name]
+    nv = NV[name]
     x = np.asarray(x, dtype=np.float64)
     g = np.zeros(nv)                       # the shared-memory accumulators (all of dE/dx at the end)
-    xr, gr = (x.copy(), np.zeros(nv)) if phases else (x, g)
+    xr, gr = x.copy(), np.zeros(nv)        # register slots: orbit sums / orbit gradients of the current phase
     f = words.view(np.float64)
-    masks = interpret.masks[name] if masks is None else masks
     nm = len(masks)
+    t_base = OP_MASK + 2 * nm
+    s_base = t_base + len(phases)
+    d_base = s_base + MAX_DEPTH
     pc = 1
     v, a = 0.0, 1.0
     stack = []
@@ -474,8 +388,7 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
     while True:
         hdr = int(words[pc])
         op, k = hdr & 0xFFFFFFFF, hdr >> 32
-        if LOOKAHEAD:
-            op, nxt = nxt, op
+        op, nxt = nxt, op
         if op == OP_END:
             return v, g
         if op == OP_NEXT:
@@ -493,27 +406,24 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
             pc += 2
         elif op < OP_MASK + nm:
             m = masks[op - OP_MASK]
-            q = pc + 1
-            n = 0
-            for b in m:
-                for j in blocks[b]:
-                    c = f[q]
-                    q += 1
-                    n += 1
-                    v += c * xr[j]
-                    gr[j] += c * a
-            pc += 1 + (n if n % 2 else n + 1)
-        elif phases and op >= OP_MASK + 2 * nm + len(phases):       # SIBLING_d: LEAVE k_old + ENTER k_new, c0
-            w = v
-            v, a, xk = stack.pop()
-            v += xk * w
-            g[k >> 8] += a * w
-            stack.append((v, a, x[k & 0xFF]))
-            a = a * x[k & 0xFF]
-            v = f[pc + 1]
-            pc += 2
-        elif phases and op >= OP_MASK + 2 * nm:  # transition: scatter the gradients of phase p, load phase p + 1
-            p = op - OP_MASK - 2 * nm
+            for q, j in enumerate(m):
+                c = f[pc + 1 + q]
+                v += c * xr[j]
+                gr[j] += c * a
+            pc += rec_words(len(m))
+        elif op < t_base:                                   # LEAFNODE_h: ENTER k, const; MASK_h; LEAVE k
+            m = masks[op - OP_MASK - nm]
+            a2 = a * x[k]
+            u = f[pc + 1]
+            for q, j in enumerate(m):
+                c = f[pc + 2 + q]
+                u += c * xr[j]
+                gr[j] += c * a2
+            v += x[k] * u
+            g[k] += a * u
+            pc += rec_words(1 + len(m))
+        elif op < s_base:                                   # TRANSITION_p
+            p = op - t_base
             for o in phases[p]:
                 for i in o:
                     g[i] += gr[o[0]]
@@ -524,77 +434,63 @@ def interpret(name, words, x, chunk_bytes, masks=None, combos=(), phases=None):
                         xr[o[0]] += x[i]
                     gr[o[0]] = 0.0
             pc += 2
-        else:                                   # fused leaf node(s): ENTER k, const; MASK_m; LEAVE k  (x2 for PAIR_m)
-            pair = OP_MASK + 2 * nm <= op < OP_MASK + 3 * nm
-            if op >= OP_MASK + 3 * nm:
-                m = masks[combos[op - OP_MASK - 3 * nm][0]]
-            elif pair:
-                m = masks[pair_masks(name, masks, 1 << 30)[op - OP_MASK - 2 * nm]]
-            else:
-                m = masks[op - OP_MASK - nm]
-            q = pc + 1
-            n = 0
-            for kk in ((k & 0xFF, k >> 8) if pair else (k,)):
+        elif op < d_base:                                   # SIBLING_d: LEAVE k_old + ENTER k_new, c0
+            w = v
+            v, a, xk = stack.pop()
+            v += xk * w
+            g[k >> 8] += a * w
+            stack.append((v, a, x[k & 0xFF]))
+            a = a * x[k & 0xFF]
+            v = f[pc + 1]
+            pc += 2
+        else:                                               # DUAL_i: two sibling leaf nodes, interleaved payload
+            m = masks[dual[op - d_base]]
+            for s, kk in enumerate((k & 0xFF, k >> 8)):
                 a2 = a * x[kk]
-                u = f[q]
-                q += 1
-                n += 1
-                for b in m:
-                    for j in blocks[b]:
-                        c = f[q]
-                        q += 1
-                        n += 1
-                        u += c * xr[j]
-                        gr[j] += c * a2
+                u = f[pc + 1 + s]
+                for q, j in enumerate(m):
+                    c = f[pc + 3 + 2 * q + s]
+                    u += c * xr[j]
+                    gr[j] += c * a2
                 v += x[kk] * u
                 g[kk] += a * u
-            pc += 1 + (n if n % 2 else n + 1)
+            pc += rec_words(2 + 2 * len(m))
 
 
-interpret.masks = {}
-
-
-def hexd(v):
-    return "0d%016X" % struct.unpack("<Q", struct.pack("<d", float(v)))[0]
-
-
-def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min_blocks=1, nacc=2, ahead=4, piece=16,
-               opaque=True, cmem=False, repeat=1, npair=0, combos=(), split_tail=False, phases=None, sib=False,
-               fall=(), npre=6, fall_copies=2):
+def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_blocks=1, piece=64, fall=(), npre=8,
+               fall_copies=2, group=4):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
 
-    One thread per tuple; x / g of the class variables and the adjoints in registers.  The stream is staged through a
-    double-buffered shared-memory window: every thread fetches `piece` bytes of chunk c+1 into registers when chunk c
-    starts, stores them when chunk c ends (OP_NEXT) and one bar.sync flips the buffers -- the global-load latency is
-    never exposed, the handlers read coefficients with broadcast ld.shared (every lane the same address).
+    One thread per tuple; x / g slots and the adjoints in registers.  The stream is staged through a double-buffered
+    shared-memory window: when chunk c starts every thread issues cp.async copies of its 16-byte pieces of chunk c + 1
+    straight into the idle buffer; at NEXT a cp.async.wait_all and one bar.sync flip the buffers.  Handlers read
+    coefficients with broadcast ld.shared.v2.f64 (every lane the same address).  Every handler pre-loads the next
+    record's header and first `npre` payload words -- before its own g_k store, which ptxas could not move them across --
+    and ends with its own brx.idx on the opcode it already knew on entry.
     Returns (lines, dynamic shared bytes)."""
-    blocks = [[j] for j in range(nv)] if phases else BLOCKS[name]      # symmetry mode: a mask is a tuple of slots
     NT = block
     CH = NT * piece                    # chunk bytes = one piece per thread
-    # EXPERIMENT (cmem=True): the whole stream sits in the constant bank (<= 64 KB) and is read with uniform ld.const;
-    # no shared-memory staging, no OP_NEXT.  `repeat` re-runs the stream (timing experiments with truncated streams).
-    LD, SP, SPV = ("ld.const", "%cp", "%cp") if cmem else ("ld.shared", "%sp", "%spv")
-    cset = set(class_vars)
-    pfld = "ld.global.nc.v2.f64 {%pf0, %pf1}" if piece == 16 else "ld.global.nc.f64 %pf0"
-    pfst = "{%pf0, %pf1}" if piece == 16 else "%pf0"
-    pfty = "v2.f64" if piece == 16 else "f64"
-    # smem: x copy | g accumulators [| second g accumulator array (split_tail)] | 2 stream buffers
-    SX, SG = 0, nv * NT * 8
-    SG2 = 2 * nv * NT * 8
-    SB = (3 if split_tail else 2) * nv * NT * 8
+    assert piece > 16 and piece % 16 == 0 and npre % 2 == 0
+    nm = len(masks)
+    t_base = OP_MASK + 2 * nm
+    s_base = t_base + len(phases)
+    d_base = s_base + MAX_DEPTH
+    n_ops = d_base + len(dual)
+    SG = nv * NT * 8                   # smem: x copy | g accumulators | 2 stream buffers
+    SB = 2 * nv * NT * 8
     out = []
     w = out.append
     w(f".visible .entry {entry}(.param .u64 p_x, .param .u64 p_out, .param .u32 p_n, .param .u32 p_ld, .param .u32 p_acc)")
     w(f".maxntid {NT}, 1, 1")
     w(f".minnctapersm {min_blocks}")
     w("{")
-    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<64>, %vc, %vd, %ac, %w, %cst, %gk, %one, %u0, %u1, %a0, %xk0, %pf0, %pf1, %n<16>, %u2, %u3;")
+    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<72>, %vc, %vd, %ac, %w, %gk, %one, %u0, %u1, %u2, %u3, %a0, %a1, %xk0, %n<16>;")
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
-    w(".reg .u32 %sp, %spv, %z, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %a1, %xkb, %gkb;")
-    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc; .reg .f64 %xkn; .reg .u32 %addrn;")
+    w(".reg .u32 %sp, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %xkb, %gkb;")
+    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc;")
     w("ld.param.u32 %acc, [p_acc]; setp.ne.u32 %pacc, %acc, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
     w("cvta.to.global.u64 %px, %px; cvta.to.global.u64 %po, %po;")
@@ -608,215 +504,116 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("shl.b32 %sx, %r2, 3; add.u32 %sx, %sx, %r3;")             # &xs[0][tid]
     w(f"add.u32 %sg, %sx, {SG};")                                  # &gs[0][tid]
     w(f"add.u32 %bufcur, %r3, {SB}; add.u32 %bufoth, %bufcur, {CH};")
-    ASYNC = piece > 16            # chunks > 4 KB: cp.async straight into the idle buffer (no staging registers)
-    assert piece % 16 == 0 or not ASYNC
 
     def async_fetch(buf):
         """this thread's 16-byte pieces of the chunk at %gs -> shared buffer `buf` (asynchronously)"""
         w(f"add.u32 %addr, {buf}, %mine;")
         for q in range(piece // 16):
             w(f"cp.async.ca.shared.global [%addr+{q * NT * 16}], [%gs+{q * NT * 16}], 16;")
-    w(f"mul.lo.u32 %mine, %r2, {16 if ASYNC else piece};")           # this thread's piece of a chunk
-    # stream chunk 0 -> buffer 0, chunk 1 -> registers (ASYNC: -> buffer 1, in flight)
+    w("mul.lo.u32 %mine, %r2, 16;")
+    # stream chunk 0 -> buffer 0 (waited for), chunk 1 -> buffer 1 (in flight)
     w(f"mov.u64 %gs, {stream}; cvta.to.global.u64 %gs, %gs; cvt.u64.u32 %off, %mine; add.u64 %gs, %gs, %off;")
-    if ASYNC:
-        async_fetch("%bufcur")
-        w("cp.async.wait_all;")
-        w(f"add.u64 %gs, %gs, {CH};")
-        async_fetch("%bufoth")
-    else:
-        w(f"{pfld}, [%gs];")
-        w(f"add.u32 %addr, %bufcur, %mine; st.shared.{pfty} [%addr], {pfst};")
-        w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
+    async_fetch("%bufcur")
+    w("cp.async.wait_all;")
+    w(f"add.u64 %gs, %gs, {CH};")
+    async_fetch("%bufoth")
     w("mov.f64 %one, 0d3FF0000000000000;")
-    if opaque:
-        # word 0 of the stream is padding (zero).  Reading one of its halves at a thread-dependent address gives a zero
-        # ptxas cannot prove uniform: payload loads through %spv = %sp + 0 then stay in vector registers instead of
-        # being moved to uniform registers one R2UR per 32 bits (580 R2UR vs 2135 DFMA in the static SASS otherwise).
-        w(f"mov.u64 %off, {stream}; cvta.to.global.u64 %off, %off; and.b32 %r3, %r2, 1; mul.wide.u32 %ldb, %r3, 4;")
-        w("add.u64 %off, %off, %ldb; ld.global.nc.u32 %z, [%off]; mul.wide.u32 %ldb, %ld, 8;")
-    else:
-        w("mov.u32 %z, 0;")
     for i in range(nv):
         w(f"ld.global.nc.f64 %x{i}, [%px]; add.u64 %px, %px, %ldb;")
     for i in range(nv):
         w(f"st.shared.f64 [%sx+{i * NT * 8}], %x{i}; st.shared.f64 [%sg+{i * NT * 8}], 0d0000000000000000;")
-        if split_tail:
-            w(f"st.shared.f64 [%sg+{i * NT * 8 + SG2 - SG}], 0d0000000000000000;")
-        if i in cset:
-            w(f"mov.f64 %g{i}, 0d0000000000000000;")
+        w(f"mov.f64 %g{i}, 0d0000000000000000;")
     w("mov.f64 %vc, 0d0000000000000000; mov.f64 %vd, 0d0000000000000000; mov.f64 %ac, %one;")
     w("bar.sync 0;")
-    w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
-    n_pairs_ops = len(pair_masks(name, masks, npair)) if npair else 0
-    n_ops = OP_MASK + 3 * len(masks) + len(combos) if combos else OP_MASK + 2 * len(masks) + n_pairs_ops
-    if phases:
-        assert not combos and not npair
-        n_ops = OP_MASK + 2 * len(masks) + len(phases) + (MAX_DEPTH if sib else 0)
-    NPRE = int(os.environ.get("PIP_NPRE", npre))  # payload words of the NEXT record pre-loaded by every handler
-    targets = [f"H{i}" for i in range(n_ops)]
-    if combos:                                   # unused pair slots of the opcode table fall through to END
-        for i in range(OP_MASK + 2 * len(masks) + n_pairs_ops, OP_MASK + 3 * len(masks)):
-            targets[i] = f"H{OP_END}"
-    w("TBL: .branchtargets " + ", ".join(targets) + ";")
+    w("add.u32 %sp, %bufcur, 8;")
+    NPRE = npre                                   # payload words of the NEXT record pre-loaded by every handler
+    w("TBL: .branchtargets " + ", ".join(f"H{i}" for i in range(n_ops)) + ";")
 
-    XKPRE = bool(int(os.environ.get("PIP_XKPRE", "0")))   # every handler loads x_k of the NEXT record before dispatching
-
-    def next_xk():
-        if XKPRE:
-            w(f"and.b32 %addrn, %nk, 255; mad.lo.u32 %addrn, %addrn, {NT * 8}, %sx; ld.shared.f64 %xkn, [%addrn];")
-
-    def preload(byte_off):
-        """first NPRE payload words of the record at %sp+byte_off -> %n0..%n5 (garbage past short records: unused)"""
-        for q in range(0, NPRE, 2):
-            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{byte_off + 8 + 8 * q}];")
-
-    DISP = "%op" if LOOKAHEAD else "%nop"
+    def preload(byte_off, start=0):
+        """payload words start..NPRE of the record at %sp+byte_off -> %n regs (garbage past short records: unused)"""
+        for q in range(start, NPRE, 2):
+            w(f"ld.shared.v2.f64 {{%n{q}, %n{q + 1}}}, [%sp+{byte_off + 8 + 8 * q}];")
 
     def head(nwords):
         """current k <- header fetched by the previous handler; fetch the next header"""
-        w("mov.u32 %k, %nk;")
-        if LOOKAHEAD:
-            w("mov.u32 %op, %nop;")
-        if XKPRE:
-            w("mov.f64 %xk0, %xkn;")
-        w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}+{8 * nwords}];")
-        next_xk()
+        w("mov.u32 %k, %nk; mov.u32 %op, %nop;")
+        w(f"ld.shared.v2.u32 {{%nop, %nk}}, [%sp+{8 * nwords}];")
 
-    FALL_COPIES = int(os.environ.get("PIP_FALL_COPIES", fall_copies))
-    SELFBR = bool(int(os.environ.get("PIP_SELF_BRANCH", "0")))
-    cur_label = [None, None]
     fall_state = [None]
 
-    EARLY = bool(int(os.environ.get("PIP_EARLY_PRELOAD", "1")))
-    # ptxas cannot prove that the per-thread st.shared of g_k does not alias the stream window, so a preload that follows
-    # the store in program order can never be scheduled above it (and its latency ends up exposed, as R2UR /
-    # short-scoreboard stalls, at the end of the short handlers): with EARLY every handler issues its preloads of the
-    # next record BEFORE its store.
-
-    def early_preload(nwords, start=0):
-        """preload pairs start.. of the next record now; returns the `preloaded` argument for tail()"""
-        if not EARLY:
-            return start
-        for q in range(start, NPRE, 2):
-            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * q}];")
-        return NPRE
-
     def tail(nwords, preloaded=0):
-        for q in range(preloaded, NPRE, 2):
-            w(f"{LD}.v2.f64 {{%n{q}, %n{q + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * q}];")
-        if cmem:
-            w(f"add.u64 %cp, %cp, {8 * nwords};")
-        else:
-            w(f"add.u32 %sp, %sp, {8 * nwords}; add.u32 %spv, %spv, {8 * nwords};")
-        if SELFBR and cur_label[0] is not None:
-            w(f"setp.eq.u32 %pself, {DISP}, {cur_label[1]}; @%pself bra.uni {cur_label[0]};")
+        preload(8 * nwords, preloaded)
+        w(f"add.u32 %sp, %sp, {8 * nwords};")
         if fall_state[0] is not None:
             # a second copy of this handler follows: when the next record has the same opcode no branch is taken
-            w(f"setp.ne.u32 %pself, {DISP}, {fall_state[0]}; @%pself brx.idx {DISP}, TBL;")
+            w(f"setp.ne.u32 %pself, %op, {fall_state[0]}; @%pself brx.idx %op, TBL;")
             return
-        w(f"brx.idx {DISP}, TBL;")              # per-handler dispatch: ptxas can hoist the jump-table read
-
-    SEPTAIL = bool(int(os.environ.get("PIP_SEPTAIL", "0")))     # experiment: see block_handler
-    TRICKLE = int(os.environ.get("PIP_TRICKLE", "4"))     # preload word pair q of the next record right after its last use
-    FAKE = bool(int(os.environ.get("PIP_FAKE_COEF", "0")))      # timing experiment only: skip the payload loads
-    ALIAS = int(os.environ.get("PIP_FAKE_ALIAS", "0"))          # timing experiment only: fold x/g onto N registers
+        w("brx.idx %op, TBL;")              # per-handler dispatch: ptxas hoists the jump-table read
 
     def coef(i):
-        if FAKE:
-            return f"%n{i % NPRE}"
         return f"%n{i}" if i < NPRE else f"%c{i - NPRE}"
 
-    if cmem:
-        w(f".reg .u64 %cp; .reg .u32 %rep; .reg .pred %prep; mov.u32 %rep, {repeat};")
-        w("RESTART:")
-        w(f"mov.u64 %cp, {stream}; add.u64 %cp, %cp, 8;")
-    if LOOKAHEAD:
-        assert not opaque and not cmem
-        w("ld.shared.u32 %op, [%bufcur];")         # word 0 of the stream: the first opcode
-    w(f"{LD}.v2.u32 {{%nop, %nk}}, [{SP}];")
-    next_xk()
+    w("ld.shared.u32 %op, [%bufcur];")         # word 0 of the stream: the first opcode
+    w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
     preload(0)
-    w(f"brx.idx {DISP}, TBL;")
+    w("brx.idx %op, TBL;")
     # ---- END
     w(f"H{OP_END}:")
-    if cmem:
-        w("sub.u32 %rep, %rep, 1; setp.ne.u32 %prep, %rep, 0; @%prep bra.uni RESTART;")
     w("bra.uni FINISH;")
-    # ---- NEXT: publish chunk c+1 (held in registers since chunk c began), flip buffers, start fetching chunk c+2
+    # ---- NEXT: chunk c + 1 has arrived in the idle buffer: flip, start fetching chunk c + 2 into the buffer just left
     w(f"H{OP_NEXT}:")
-    if LOOKAHEAD:
-        w("mov.u32 %op, %nop;")
-    if ASYNC:
-        w("cp.async.wait_all;")
-    else:
-        w(f"add.u32 %addr, %bufoth, %mine; st.shared.{pfty} [%addr], {pfst};")
+    w("mov.u32 %op, %nop;")
+    w("cp.async.wait_all;")
     w("bar.sync 0;")
     w("mov.u32 %addr, %bufcur; mov.u32 %bufcur, %bufoth; mov.u32 %bufoth, %addr;")
-    if ASYNC:                                   # everyone has left the old buffer: refill it with chunk c + 2
-        w(f"add.u64 %gs, %gs, {CH};")
-        async_fetch("%bufoth")
-    else:
-        w(f"add.u64 %gs, %gs, {CH}; {pfld}, [%gs];")
-    w("add.u32 %sp, %bufcur, 8; add.u32 %spv, %sp, %z;")
+    w(f"add.u64 %gs, %gs, {CH};")
+    async_fetch("%bufoth")
+    w("add.u32 %sp, %bufcur, 8;")
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
-    next_xk()
     preload(0)
-    w(f"brx.idx {DISP}, TBL;")
+    w("brx.idx %op, TBL;")
     # ---- ENTER_d  (payload: const in %n0)
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_ENTER + d - 1}:")
         head(2)
-        if XKPRE:
-            w(f"mov.f64 %xk{d}, %xk0;")
-        else:
-            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk{d}, [%addr];")
+        w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk{d}, [%addr];")
         w(f"mov.f64 %vs{d}, %vc; mov.f64 %vt{d}, %vd; mov.f64 %as{d}, %ac;")
         w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
-        pre = early_preload(2)
+        preload(16)
         w(f"mul.rn.f64 %ac, %ac, %xk{d};")
-        tail(2, pre)
+        tail(2, NPRE)
     # ---- LEAVE_d
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_LEAVE + d - 1}:")
         head(2)
         w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
-        pre = early_preload(2)
+        preload(16)
         w("add.rn.f64 %w, %vc, %vd;")
         w(f"mov.f64 %ac, %as{d};")
         w(f"fma.rn.f64 %vc, %xk{d}, %w, %vs{d}; mov.f64 %vd, %vt{d};")
         w("fma.rn.f64 %gk, %ac, %w, %gk; st.shared.f64 [%addr], %gk;")
-        tail(2, pre)
+        tail(2, NPRE)
 
-    # ---- MASK_m and fused LEAFNODE_m
-    def block_handler(label, m, fused, static_k=None):
-        """Hand-scheduled for in-order issue (assembled with ptxas -O1, which keeps this order): loads first, then the
-        value FMAs on `nacc` independent chains, the adjoint product as late as its shared-memory operand allows, and the
-        chain reduction + parent update interleaved with the (mutually independent) gradient FMAs."""
+    # ---- MASK_h and fused LEAFNODE_h
+    def block_handler(label, m, fused):
+        """loads first, then `group` value FMAs on two chains alternating with the `group` gradient FMAs of the same
+        slots; once both FMAs of a 16-byte payload piece are issued its registers are dead and the same piece of the NEXT
+        record is loaded into them; the chain reduction + parent update close the record."""
         w(f"{label}:")
-        cur_label[0], cur_label[1] = (label, int(label[1:])) if (fused and label[1:].isdigit()) else (None, None)
-        vars_ = [j for b in m for j in blocks[b]]
-        slots = ([None] if fused else []) + vars_          # None = the node constant (first payload word)
+        slots = ([None] if fused else []) + list(m)          # None = the node constant (first payload word)
         n = len(slots)
         nwords = rec_words(n)
         head(nwords)
-        xk, gk = ("%xk0", "%gk") if static_k is None else (f"%x{static_k}", f"%g{static_k}")
-        if fused and static_k is None:
-            if not XKPRE:
-                w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
-            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
-            if split_tail:
-                w(f"ld.shared.f64 %gkb, [%addr+{SG2 - SG}];")
-        for i in range(NPRE, n if not FAKE else 0, 2):     # the rest of this record's payload
-            if i + 1 < n:
-                w(f"{LD}.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [{SPV}+{8 + 8 * i}];")
-            else:
-                w(f"{LD}.f64 {coef(i)}, [{SPV}+{8 + 8 * i}];")
-        assert n - NPRE <= 32
         if fused:
-            acc, adj = [f"%u{q}" for q in range(max(1, nacc))], "%a0"
-        else:
-            acc, adj = (["%vc", "%vd"] + [f"%u{q}" for q in range(2, max(2, nacc))])[:max(1, nacc)], "%ac"
+            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
+            w(f"mad.lo.u32 %addr, %k, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
+        for i in range(NPRE, n, 2):                          # the rest of this record's payload
+            if i + 1 < n:
+                w(f"ld.shared.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [%sp+{8 + 8 * i}];")
+            else:
+                w(f"ld.shared.f64 {coef(i)}, [%sp+{8 + 8 * i}];")
+        assert n - NPRE <= 64
+        acc, adj = (["%u0", "%u1"], "%a0") if fused else (["%vc", "%vd"], "%ac")
         started = set() if fused else {"%vc", "%vd"}
         vops, gops = [], []
         for i, j in enumerate(slots):
@@ -825,181 +622,105 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                 vops.append(f"mov.f64 %u0, {c};")
                 started.add("%u0")
                 continue
-            a = acc[i % len(acc)]
-            if ALIAS:
-                j = j % ALIAS
+            a = acc[i % 2]
             if a in started:
                 vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
             else:
                 vops.append(f"mul.rn.f64 {a}, {c}, %x{j};")
                 started.add(a)
             gops.append(f"fma.rn.f64 %g{j}, {c}, {adj}, %g{j};")
-        # reduction of the value chains (+ parent update for fused nodes)
-        rops = []
-        if not fused:
-            for extra, base in (("%u2", "%vc"), ("%u3", "%vd")):
-                if extra in acc and extra in started:
-                    rops.append(f"add.rn.f64 {base}, {base}, {extra};")
-        elif split_tail and static_k is None and len([a for a in acc if a in started]) == 2:
-            # no reduction: each value chain feeds its own parent accumulator and its own g_k accumulator array, so the
-            # record ends with independent FMA -> STS pairs instead of a DADD -> DFMA -> STS chain
-            rops += [f"fma.rn.f64 %vc, {xk}, %u0, %vc;", f"fma.rn.f64 %vd, {xk}, %u1, %vd;",
-                     "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u1, %gkb;",
-                     "st.shared.f64 [%addr], %gk;", f"st.shared.f64 [%addr+{SG2 - SG}], %gkb;"]
-        elif SEPTAIL and static_k is None and len([a for a in acc if a in started]) >= 2:
-            # the last reduction level is not taken: the two partial sums go separately into the parent's two value
-            # accumulators and (back to back) into g_k -- one FP64 instruction more, one dependent level less
-            live = [a for a in acc if a in started]
-            while len(live) > 2:
-                nxt = []
-                for q in range(0, len(live) - 1, 2):
-                    rops.append(f"add.rn.f64 {live[q]}, {live[q]}, {live[q + 1]};")
-                    nxt.append(live[q])
-                if len(live) % 2:
-                    nxt.append(live[-1])
-                live = nxt
-            rops += [f"fma.rn.f64 %vc, {xk}, {live[0]}, %vc;", f"fma.rn.f64 %vd, {xk}, {live[1]}, %vd;",
-                     f"fma.rn.f64 %gk, %ac, {live[0]}, %gk;", f"fma.rn.f64 %gk, %ac, {live[1]}, %gk;",
-                     "st.shared.f64 [%addr], %gk;"]
-        else:
-            live = [a for a in acc if a in started]
-            while len(live) > 1:
-                nxt = []
-                for q in range(0, len(live) - 1, 2):
-                    rops.append(f"add.rn.f64 {live[q]}, {live[q]}, {live[q + 1]};")
-                    nxt.append(live[q])
-                if len(live) % 2:
-                    nxt.append(live[-1])
-                live = nxt
-            rops.append(f"fma.rn.f64 %vc, {xk}, {live[0]}, %vc;")
-            rops.append(f"fma.rn.f64 {gk}, %ac, {live[0]}, {gk};")
-            if static_k is None:
-                rops.append("st.shared.f64 [%addr], %gk;")
-        if TRICKLE and fused and static_k is None:
-            # slot pairs in payload order; once both FMAs of the two slots of a 16-byte payload piece are issued the
-            # piece's registers are dead and the same piece of the NEXT record is loaded into them
-            w(f"mul.rn.f64 %a0, %ac, {xk};")
-            done = 0
-            vi = gi = 0
-            for q in range(0, n, TRICKLE):
-                cnt = min(TRICKLE, n - q)
-                for u in range(cnt):
-                    w(vops[q + u])
-                for u in range(cnt):
-                    if slots[q + u] is not None:
-                        w(gops[gi])
-                        gi += 1
-                for p2 in range(q, q + cnt + (cnt & 1), 2):
-                    if p2 + 1 < NPRE:
-                        w(f"{LD}.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [{SPV}+{8 * nwords + 8 + 8 * p2}];")
-                        done = p2 + 2
-            done = early_preload(nwords, done)
-            for r in rops:
-                w(r)
-            tail(nwords, done)
-            return
-        # emit: value ops, adjoint product after the first few, then gradient ops with the reduction spread between
-        npre_v = min(len(vops), NPRE)
-        for op in vops[:npre_v]:
-            w(op)
         if fused:
-            w(f"mul.rn.f64 %a0, %ac, {xk};")
-        for op in vops[npre_v:]:
-            w(op)
-        gap = max(1, len(gops) // (len(rops) + 1)) if rops else len(gops) + 1
+            w("mul.rn.f64 %a0, %ac, %xk0;")
+        done = 0
         gi = 0
-        for r in rops:
-            for _ in range(gap):
-                if gi < len(gops):
+        for q in range(0, n, group):
+            cnt = min(group, n - q)
+            for u in range(cnt):
+                w(vops[q + u])
+            for u in range(cnt):
+                if slots[q + u] is not None:
                     w(gops[gi])
                     gi += 1
-            w(r)
-        for op in gops[gi:]:
-            w(op)
-        tail(nwords)
+            for p2 in range(q, q + cnt + (cnt & 1), 2):
+                if p2 + 1 < NPRE:
+                    w(f"ld.shared.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [%sp+{8 * nwords + 8 + 8 * p2}];")
+                    done = p2 + 2
+        preload(8 * nwords, done)
+        if fused:
+            if "%u1" in started:
+                w("add.rn.f64 %u0, %u0, %u1;")
+            w("fma.rn.f64 %vc, %xk0, %u0, %vc;")
+            w("fma.rn.f64 %gk, %ac, %u0, %gk;")
+            w("st.shared.f64 [%addr], %gk;")
+        tail(nwords, NPRE)
 
-    def pair_handler(label, m):
-        """two LEAFNODE_m records at once: A accumulates on %u0/%u1 -> %vc, B on %u2/%u3 -> %vd"""
+    def dual_handler(label, m):
+        """two sibling LEAFNODE records A, B of the same handler.  Payload words: c0_A, c0_B, then (c_Aj, c_Bj) per slot.
+        A accumulates on %u0 / %u1 and updates the parent through %vc, B on %u2 / %u3 through %vd; the two value FMAs of
+        a slot are adjacent and share x_j (operand reuse), the gradient FMAs of a group run A-then-B so that each
+        adjoint stays in the reuse cache."""
         w(f"{label}:")
-        vars_ = [j for b in m for j in blocks[b]]
-        n1 = 1 + len(vars_)
-        n = 2 * n1
-        nwords = rec_words(n)
+        n = len(m)
+        nw = 2 + 2 * n                                       # payload words
+        nwords = rec_words(nw)
         head(nwords)
         w("and.b32 %ka, %k, 255; shr.u32 %kb, %k, 8;")
         w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sx; ld.shared.f64 %xk0, [%addr];")
         w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
         w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
         w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sg; ld.shared.f64 %gkb, [%addrb];")
-        for i in range(NPRE, n, 2):
-            if i + 1 < n:
-                w(f"{LD}.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [{SPV}+{8 + 8 * i}];")
-            else:
-                w(f"{LD}.f64 {coef(i)}, [{SPV}+{8 + 8 * i}];")
-        assert n - NPRE <= 48
-        seq = {}
-        for tag, base, accs, adj in (("A", 0, ["%u0", "%u1"], "%a0"), ("B", n1, ["%u2", "%u3"], "%a1")):
-            vops, gops = [f"mov.f64 {accs[0]}, {coef(base)};"], []
-            started = {accs[0]}
-            for i, j in enumerate(vars_):
-                c = coef(base + 1 + i)
-                a = accs[(i + 1) % 2]
-                if a in started:
-                    vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
-                else:
-                    vops.append(f"mul.rn.f64 {a}, {c}, %x{j};")
-                    started.add(a)
-                gops.append(f"fma.rn.f64 %g{j}, {c}, {adj}, %g{j};")
-            seq[tag] = (vops, gops, len(started) > 1)
-        for a_op, b_op in zip(seq["A"][0], seq["B"][0]):
-            w(a_op)
-            w(b_op)
+        for i in range(NPRE, nw, 2):
+            w(f"ld.shared.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [%sp+{8 + 8 * i}];")
+        w("mov.f64 %u0, %n0; mov.f64 %u2, %n1;")
         w("mul.rn.f64 %a0, %ac, %xk0;")
         w("mul.rn.f64 %a1, %ac, %xkb;")
-        if seq["A"][2]:
+        started = {"%u0", "%u2"}
+        done = 0
+        for q in range(0, n, group):
+            js = list(range(q, min(q + group, n)))
+            for j in js:                                     # value FMAs: A and B of one slot adjacent (x_j reused)
+                for s, accs in ((0, ("%u0", "%u1")), (1, ("%u2", "%u3"))):
+                    a, c = accs[(j + 1) % 2], coef(2 + 2 * j + s)
+                    if a in started:
+                        w(f"fma.rn.f64 {a}, {c}, %x{m[j]}, {a};")
+                    else:
+                        w(f"mul.rn.f64 {a}, {c}, %x{m[j]};")
+                        started.add(a)
+            for s, adj in ((0, "%a0"), (1, "%a1")):          # gradient FMAs of the group: all of A, then all of B
+                for j in js:
+                    w(f"fma.rn.f64 %g{m[j]}, {coef(2 + 2 * j + s)}, {adj}, %g{m[j]};")
+            # payload words < 2 + 2 * (js[-1] + 1) are dead now: refill their registers with the next record's words
+            dead = 2 + 2 * (js[-1] + 1)
+            while done + 2 <= min(dead, NPRE):
+                w(f"ld.shared.v2.f64 {{%n{done}, %n{done + 1}}}, [%sp+{8 * nwords + 8 + 8 * done}];")
+                done += 2
+        preload(8 * nwords, done)
+        if "%u1" in started:
             w("add.rn.f64 %u0, %u0, %u1;")
+        if "%u3" in started:
             w("add.rn.f64 %u2, %u2, %u3;")
-        rops = ["fma.rn.f64 %vc, %xk0, %u0, %vc;", "fma.rn.f64 %vd, %xkb, %u2, %vd;",
-                "fma.rn.f64 %gk, %ac, %u0, %gk;", "fma.rn.f64 %gkb, %ac, %u2, %gkb;",
-                "st.shared.f64 [%addr], %gk;", "st.shared.f64 [%addrb], %gkb;"]
-        # all gradient FMAs of A (adjoint %a0 stays in the operand-reuse cache), then all of B: zipping them would
-        # alternate the adjoint operand and put two dependent updates of the same g_j back to back
-        gops = seq["A"][1] + seq["B"][1]
-        gap = max(1, len(gops) // (len(rops) + 1))
-        gi = 0
-        for r in rops:
-            for _ in range(gap):
-                if gi < len(gops):
-                    w(gops[gi])
-                    gi += 1
-            w(r)
-        for op in gops[gi:]:
-            w(op)
-        tail(nwords)
+        w("fma.rn.f64 %vc, %xk0, %u0, %vc;")
+        w("fma.rn.f64 %vd, %xkb, %u2, %vd;")
+        w("fma.rn.f64 %gk, %ac, %u0, %gk;")
+        w("fma.rn.f64 %gkb, %ac, %u2, %gkb;")
+        w("st.shared.f64 [%addr], %gk;")
+        w("st.shared.f64 [%addrb], %gkb;")
+        tail(nwords, NPRE)
 
     for mi, m in enumerate(masks):
         block_handler(f"H{OP_MASK + mi}", m, False)
     for mi, m in enumerate(masks):
-        op = OP_MASK + len(masks) + mi
-        if op in fall:
-            # FALL_COPIES back-to-back copies: every copy but the last falls through into the next one when the next
-            # record has the same opcode (runs of 2, 3 and 4 equal records are the rule: symmetry-related siblings)
-            for c in range(FALL_COPIES):
-                fall_state[0] = op if c + 1 < FALL_COPIES else None
-                block_handler(f"H{op}" + ("" if c == 0 else "BCDEFGH"[c - 1]), m, True)
-        else:
-            block_handler(f"H{op}", m, True)
-    for ci, (mi, kk) in enumerate(combos):
-        assert kk in cset, "static node variable must be a register of this class"
-        block_handler(f"H{OP_MASK + 3 * len(masks) + ci}", masks[mi], True, static_k=kk)
-    pairable = pair_masks(name, masks, npair) if npair else []
-    for pi, mi in enumerate(pairable):
-        pair_handler(f"H{OP_MASK + 2 * len(masks) + pi}", masks[mi])
-    # ---- TRANSITION_p (symmetry mode): scatter the register gradients of phase p to every member of their orbit
-    # (shared-memory accumulators), then load the orbit sums of phase p + 1 and clear the register gradients
-    for p, orbs in enumerate(phases or []):
-        w(f"H{OP_MASK + 2 * len(masks) + p}:")
-        cur_label[0] = cur_label[1] = None
+        op = OP_MASK + nm + mi
+        copies = fall_copies if op in fall else 1
+        # back-to-back copies: every copy but the last falls through into the next one when the next record has the
+        # same opcode (runs of equal records are the rule: symmetry-related siblings)
+        for c in range(copies):
+            fall_state[0] = op if c + 1 < copies else None
+            block_handler(f"H{op}" + ("" if c == 0 else "BCDEFGH"[c - 1]), m, True)
+    # ---- TRANSITION_p: scatter the register gradients of phase p to every member of their orbit (shared-memory
+    # accumulators), then load the orbit sums of phase p + 1 and clear the register gradients
+    for p, orbs in enumerate(phases):
+        w(f"H{t_base + p}:")
         head(2)
         for o in orbs:
             for i in o:
@@ -1010,24 +731,24 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
                 for i in o[1:]:
                     w(f"ld.shared.f64 %w, [%sx+{i * NT * 8}]; add.rn.f64 %x{o[0]}, %x{o[0]}, %w;")
         tail(2)
-    # ---- SIBLING_d (symmetry mode): LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_new | k_old << 8)
-    for d in range(1, MAX_DEPTH + 1) if (phases and sib) else []:
-        w(f"H{OP_MASK + 2 * len(masks) + len(phases) + d - 1}:")
+    # ---- SIBLING_d: LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_new | k_old << 8)
+    for d in range(1, MAX_DEPTH + 1):
+        w(f"H{s_base + d - 1}:")
         head(2)
         w("shr.u32 %ka, %k, 8; and.b32 %kb, %k, 255;")
         w(f"mad.lo.u32 %addr, %ka, {NT * 8}, %sg; ld.shared.f64 %gk, [%addr];")
-        if XKPRE:
-            w("mov.f64 %xkb, %xk0;")
-        else:
-            w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
+        w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sx; ld.shared.f64 %xkb, [%addrb];")
         w("add.rn.f64 %w, %vc, %vd;")
         w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
-        pre = early_preload(2)
+        preload(16)
         w(f"fma.rn.f64 %vs{d}, %xk{d}, %w, %vs{d};")          # the parent's value, still saved
         w(f"fma.rn.f64 %gk, %as{d}, %w, %gk; st.shared.f64 [%addr], %gk;")
         w(f"mov.f64 %xk{d}, %xkb; mul.rn.f64 %ac, %as{d}, %xkb;")
-        tail(2, pre)
-    # ---- epilogue
+        tail(2, NPRE)
+    # ---- DUAL_i
+    for di, h in enumerate(dual):
+        dual_handler(f"H{d_base + di}", masks[h])
+    # ---- epilogue: the last TRANSITION has scattered every register gradient
     w("FINISH:")
     w("@!%valid bra DONE;")
     w("add.rn.f64 %vc, %vc, %vd;")
@@ -1036,12 +757,6 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     w("st.global.f64 [%po], %vc; add.u64 %po, %po, %ldb;")
     for i in range(nv):
         w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
-        if split_tail:
-            w(f"ld.shared.f64 %gkb, [%sg+{i * NT * 8 + SG2 - SG}]; add.rn.f64 %gk, %gk, %gkb;")
-        if phases:
-            pass                                  # the last TRANSITION has already scattered the register gradients
-        elif i in cset and (not int(os.environ.get("PIP_FAKE_ALIAS", "0")) or i < int(os.environ.get("PIP_FAKE_ALIAS", "0"))):
-            w(f"add.rn.f64 %gk, %gk, %g{i};")
         w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
         w("st.global.f64 [%po], %gk; add.u64 %po, %po, %ldb;")
     w("DONE:")
@@ -1050,37 +765,31 @@ def kernel_ptx(name, entry, stream, words, masks, nv, class_vars, block=256, min
     return out, SB + 2 * CH
 
 
-CLASSES = {            # block ids per class kernel (None = one kernel with every block)
-    "pip3b": {1: None, 2: [[1, 2, 3, 4], [0, 5, 6, 7, 8]], 3: [[2, 3, 4], [5, 6, 7], [0, 1, 8]]},
-    "pip2b": {1: None, 2: [[0, 1, 2, 3, 4], [5, 6, 7, 8, 9]]},
-}
-
-
-def count_fp64(recs, masks, blocks, combos=(), phases=None):
+def count_fp64(recs, masks, phases, dual):
+    nm = len(masks)
+    t_base = OP_MASK + 2 * nm
+    s_base = t_base + len(phases)
+    d_base = s_base + MAX_DEPTH
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
-        if phases and op >= OP_MASK + 2 * len(masks) + len(phases):
+        if op >= d_base:
+            n_fp += 2 * (2 * len(masks[dual[op - d_base]]) + 4)
+            hist["dual"] += 1
+        elif op >= s_base:
             n_fp += 4
             hist["sibling"] += 1
-        elif phases and op >= OP_MASK + 2 * len(masks):
-            p = op - OP_MASK - 2 * len(masks)
+        elif op >= t_base:
+            p = op - t_base
             n_fp += sum(len(o) for o in phases[p])
             if p + 1 < len(phases):
                 n_fp += sum(len(o) - 1 for o in phases[p + 1])
             hist["transition"] += 1
-        elif op >= OP_MASK + 3 * len(masks):
-            n_fp += 2 * sum(len(blocks[b]) for b in masks[combos[op - OP_MASK - 3 * len(masks)][0]]) + 4
-            hist["static"] += 1
-        elif op >= OP_MASK + 2 * len(masks):
-            pm = [mi for mi, m in enumerate(masks) if sum(len(blocks[b]) for b in m) <= 18]
-            n_fp += 2 * (2 * sum(len(blocks[b]) for b in masks[pm[op - OP_MASK - 2 * len(masks)]]) + 4)
-            hist["pair"] += 1
-        elif op >= OP_MASK + len(masks):
-            n_fp += 2 * sum(len(blocks[b]) for b in masks[op - OP_MASK - len(masks)]) + 4
+        elif op >= OP_MASK + nm:
+            n_fp += 2 * len(masks[op - OP_MASK - nm]) + 4
             hist["leafnode"] += 1
         elif op >= OP_MASK:
-            n_fp += 2 * sum(len(blocks[b]) for b in masks[op - OP_MASK])
+            n_fp += 2 * len(masks[op - OP_MASK])
             hist["mask"] += 1
         elif op == OP_NEXT:
             pass
@@ -1093,106 +802,68 @@ def count_fp64(recs, masks, blocks, combos=(), phases=None):
     return n_fp, hist
 
 
-def generate(name, out_dir, block=256, min_blocks=1, nacc=2, ahead=4, fuse=True, n_classes=1, piece=16, opaque=False,
-             npair=0, nstatic=0, split_tail=False, sym=0, skeleton_weight=40, sib=False,
-             fall=0, npre=6, fall_copies=2):
-    """Write {name}_eval.ptx (one module, one kernel per variable class) and {name}_meta.json.
-    Returns (meta, [(words, masks) per class])."""
+def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_weight=40, fall=4, npre=8, fall_copies=2,
+             dual_max=0, group=4):
+    """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual)."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
-    blocks = BLOCKS[name]
-    classes = CLASSES[name][n_classes] or [list(range(len(blocks)))]
+    assert nv == NV[name]
     chunk = block * piece
+    recs, masks, phases, dual = serialise(name, tab, sym, skeleton_weight, dual_max)
+    nm = len(masks)
+    runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
+    lo, hi = OP_MASK + nm, OP_MASK + 2 * nm
+    fall_ops = tuple(sorted(op for op, c in runs.items() if fall and c >= fall and lo <= op < hi))
+    words = pack(recs, chunk)
+    n_fp, hist = count_fp64(recs, masks, phases, dual)
+    symbol = f"{name}_stream0"
     lines = ["// GENERATED by tools/gen_interp.py -- command-stream adjoint-Horner PIP evaluator (see the tool's docstring).",
-             ".version 8.7", ".target sm_100a", ".address_size 64", "", ".extern .shared .align 16 .b8 pip_smem[];", ""]
-    streams, kernels = [], []
-    n_fp = 0
-    hist = collections.Counter()
-    smem = 0
-    phases, fall_ops = None, ()
-    for ci, cb in enumerate(classes):
-        if sym:                                  # symmetry phases: `sym` = size of the handler library
-            assert len(classes) == 1 and not npair and not nstatic
-            recs, masks, phases = serialise_sym(name, tab, sym, skeleton_weight, sib)
-            combos = []
-            runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
-            lo, hi = OP_MASK + len(masks), OP_MASK + 2 * len(masks)
-            fall_ops = tuple(sorted(op for op, c in runs.items() if fall and c >= fall and lo <= op < hi))
-            words = pack(recs, chunk)
-            f, h = count_fp64(recs, masks, [[j] for j in range(nv)], (), phases)
-        else:
-            recs, masks = serialise(name, tab, fuse, cb, with_consts=(ci == 0), npair=npair, nstatic=nstatic)
-            combos = serialise.combos.get(name, []) if nstatic else []
-            words = pack(recs, chunk)
-            f, h = count_fp64(recs, masks, blocks, combos)
-        n_fp += f
-        hist.update(h)
-        symbol = f"{name}_stream{ci}"
-        lines.append(f".global .align 16 .b64 {symbol}[{len(words)}] = {{")
-        for i in range(0, len(words), 8):
-            lines.append(", ".join("0x%016X" % int(v) for v in words[i:i + 8]) + ("," if i + 8 < len(words) else ""))
-        lines.append("};")
-        cvars = sorted(v for b in cb for v in blocks[b])
-        entry = f"{name}_eval" if len(classes) == 1 else f"{name}_eval_c{ci}"
-        kl, sm = kernel_ptx(name, entry, symbol, words, masks, nv, cvars, block, min_blocks, nacc, ahead, piece, opaque,
-                            npair=npair, combos=combos, split_tail=split_tail, phases=phases, sib=sib,
-                            fall=fall_ops if sym else (), npre=npre, fall_copies=fall_copies)
-        lines += [""] + kl
-        smem = max(smem, sm)
-        streams.append((words, masks, combos))
-        kernels.append({"entry": entry, "vars": len(cvars), "masks": len(masks), "stream_bytes": int(words.nbytes),
-                        "fp64_instr": f})
-    interpret.masks[name] = streams[0][1]
+             ".version 8.7", ".target sm_100a", ".address_size 64", "", ".extern .shared .align 16 .b8 pip_smem[];", "",
+             f".global .align 16 .b64 {symbol}[{len(words)}] = {{"]
+    for i in range(0, len(words), 8):
+        lines.append(", ".join("0x%016X" % int(v) for v in words[i:i + 8]) + ("," if i + 8 < len(words) else ""))
+    lines.append("};")
+    entry = f"{name}_eval"
+    kl, smem = kernel_ptx(name, entry, symbol, masks, nv, phases, dual, block, min_blocks, piece, fall_ops, npre,
+                          fall_copies, group)
+    lines += [""] + kl
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
     meta = {"name": name, "block": block, "smem_bytes": smem, "fp64_instr": n_fp, "chunk_bytes": chunk,
-            "records": dict(hist), "kernels": kernels, "kind": "interp-sym" if sym else "interp",
-            "phases": phases, "handlers": [len(m) for m in streams[0][1]] if sym else None, "sib": bool(sib),
-            "lookahead": LOOKAHEAD}
+            "records": dict(hist), "kind": "interp-sym",
+            "kernels": [{"entry": entry, "vars": nv, "masks": nm, "stream_bytes": int(words.nbytes), "fp64_instr": n_fp}],
+            "phases": phases, "handlers": [len(m) for m in masks], "dual": list(dual)}
     with open(os.path.join(out_dir, f"{name}_meta.json"), "w") as fh:
         json.dump(meta, fh)
-    return meta, streams
+    return meta, words, masks, phases, dual
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=GEN)
-    ap.add_argument("--block", type=int, default=256)
-    ap.add_argument("--min-blocks", type=int, default=1)
-    ap.add_argument("--nacc", type=int, default=2)
-    ap.add_argument("--ahead", type=int, default=4, help="16-byte coefficient pieces loaded ahead of their use")
-    ap.add_argument("--no-fuse", action="store_true")
-    ap.add_argument("--classes3", type=int, default=1, help="variable classes (kernels) for the 3B polynomial")
-    ap.add_argument("--classes2", type=int, default=1)
-    ap.add_argument("--piece", type=int, default=16, choices=[8, 16, 32, 64, 128],
-                    help="stream bytes each thread stages per chunk (> 16: cp.async into the idle buffer)")
-    ap.add_argument("--npair", type=int, default=0, help="pair handlers for the N most frequent masks")
-    ap.add_argument("--nstatic2", type=int, default=0, help="2B: leaf-node handlers specialised on the node variable")
-    ap.add_argument("--nstatic3", type=int, default=0)
-    ap.add_argument("--split-tail", action="store_true", help="second g_k accumulator array: no reduction chain at record end")
-    ap.add_argument("--block2", type=int, default=0, help="2B: threads per CTA (0 = --block)")
-    ap.add_argument("--piece2", type=int, default=0, help="2B: stream bytes per thread and chunk (0 = --piece)")
-    ap.add_argument("--npre2", type=int, default=-1, help="2B: preload depth (-1 = --npre)")
-    ap.add_argument("--sym2", type=int, default=0, help="2B: symmetry phases with a library of N leaf handlers (0 = off)")
-    ap.add_argument("--sym3", type=int, default=0)
+    ap.add_argument("--only", default="", help="pip2b or pip3b (default: both)")
+    for two in ("", "2"):
+        d = {"": (256, 64, 32, 8, 0), "2": (384, 32, 12, 4, 0)}[two]
+        ap.add_argument(f"--block{two}", type=int, default=d[0], help="threads per CTA" + (" (2B)" if two else " (3B)"))
+        ap.add_argument(f"--piece{two}", type=int, default=d[1], help="stream bytes each thread stages per chunk")
+        ap.add_argument(f"--sym{two}", type=int, default=d[2], help="size of the leaf-handler library")
+        ap.add_argument(f"--npre{two}", type=int, default=d[3], help="payload words of the next record every handler pre-loads")
+        ap.add_argument(f"--dual{two}", type=int, default=d[4], help="DUAL records for handlers of at most N slots")
     ap.add_argument("--skeleton-weight", type=int, default=40)
-    ap.add_argument("--fall-copies", type=int, default=2, help="copies of a duplicated leaf handler")
-    ap.add_argument("--npre", type=int, default=6, help="payload words of the next record every handler pre-loads")
-    ap.add_argument("--sib", action="store_true", help="symmetry mode: fuse LEAVE_d + ENTER_d into SIBLING_d records")
-    ap.add_argument("--fall", type=int, default=0, help="symmetry mode: duplicate leaf handlers that follow themselves "
-                    "at least N times (no taken branch between two equal records)")
+    ap.add_argument("--fall", type=int, default=4, help="duplicate leaf handlers that follow themselves at least N times")
+    ap.add_argument("--fall-copies", type=int, default=2)
+    ap.add_argument("--group", type=int, default=4, help="slots per value / gradient FMA group inside a handler")
+    ap.add_argument("--min-blocks", type=int, default=1)
     args = ap.parse_args()
     for name in ("pip2b", "pip3b"):
-        two = name == "pip2b"
-        meta, _ = generate(name, args.out, args.block2 if two and args.block2 else args.block, args.min_blocks, args.nacc,
-                           args.ahead, not args.no_fuse, args.classes2 if two else args.classes3,
-                           args.piece2 if two and args.piece2 else args.piece, npair=args.npair,
-                           nstatic=args.nstatic2 if name == "pip2b" else args.nstatic3, split_tail=args.split_tail,
-                           sym=args.sym2 if name == "pip2b" else args.sym3, skeleton_weight=args.skeleton_weight,
-                           sib=args.sib, fall=args.fall, npre=args.npre2 if two and args.npre2 >= 0 else args.npre,
-                           fall_copies=args.fall_copies)
-        print(meta)
+        if args.only and args.only != name:
+            continue
+        t = "2" if name == "pip2b" else ""
+        meta, *_ = generate(name, args.out, getattr(args, "block" + t), args.min_blocks, getattr(args, "piece" + t),
+                            getattr(args, "sym" + t), args.skeleton_weight, args.fall, getattr(args, "npre" + t),
+                            args.fall_copies, getattr(args, "dual" + t), args.group)
+        print({k: v for k, v in meta.items() if k != "phases"})
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ out=$here/../build/mb/$tag
 mkdir -p "$out"
 (cd "$here" && env $envs python gen_interp.py "$@" --out "$out" > "$out/gen.log")
 for n in pip2b pip3b; do
+    [ -f "$out/${n}_eval.ptx" ] || continue
     ptxas -arch=sm_100a ${PTXAS_OPT:--O3} -v -lineinfo -o "$out/$n.cubin" "$out/${n}_eval.ptx" > "$out/$n.ptxas.log" 2>&1
 done
-echo "$(grep -h "registers" "$out"/*.ptxas.log | tr '\n' ' ') <- $tag"
+echo "$(grep -h "registers\|spill" "$out"/*.ptxas.log | tr '\n' ' ') <- $tag"
