@@ -43,15 +43,13 @@ int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool
     const int64_t first = order == 2 ? L.own_p0 : L.own_t0;
     const int64_t n = order == 2 ? L.own_p1 - L.own_p0 : L.own_t1 - L.own_t0;
     const int32_t* tuples = order == 2 ? L.pairs.as<int32_t>() : L.trips.as<int32_t>();
-    DeviceBuf &X = order == 2 ? ctx->x2 : ctx->x3, &R = order == 2 ? ctx->r2 : ctx->r3,
-              &O = order == 2 ? ctx->o2 : ctx->o3, &E = order == 2 ? ctx->e2 : ctx->e3,
-              &F = order == 2 ? ctx->f2 : ctx->f3;
+    DeviceBuf &X = order == 2 ? ctx->x2 : ctx->x3, &O = order == 2 ? ctx->o2 : ctx->o3,
+              &E = order == 2 ? ctx->e2 : ctx->e3, &F = order == 2 ? ctx->f2 : ctx->f3;
     ContributionIndex& ci = order == 2 ? ctx->ci2 : ctx->ci3;
     const int64_t ld = round_up(n > 0 ? n : 1, 32);
     int rc;
     std::string& err = ctx->err;
     if ((rc = X.reserve(sizeof(double) * nv * ld, err))) return rc;
-    if ((rc = R.reserve(sizeof(double) * nv * ld, err))) return rc;
     if ((rc = O.reserve(sizeof(double) * (nv + 1) * ld, err))) return rc;
     if ((rc = E.reserve(sizeof(double) * ld, err))) return rc;
     if ((rc = F.reserve(sizeof(double) * 9 * width * ld, err))) return rc;
@@ -60,19 +58,17 @@ int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool
     box.periodic = is_periodic(order == 2 ? ctx->method2 : ctx->method3);
     const int32_t* idx = ctx->idx.as<int32_t>();
     if (order == 2) {
-        launch_dimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), s);
+        launch_dimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), s);
         if (ctx->timing) cudaEventRecord(ctx->evp[0], s);
-        if ((rc = pip_launch(2, X.as<double>(), O.as<double>(), n, ld, s, &err))) return rc;
+        if ((rc = pip_launch(2, X.as<double>(), O.as<double>(), n, ld, s, &err, true))) return rc;
         if (ctx->timing) cudaEventRecord(ctx->evp[1], s);
-        launch_dimer_forces(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), O.as<double>(),
-                            E.as<double>(), F.as<double>(), s);
+        launch_dimer_forces(pos, idx, tuples, first, n, ld, box, O.as<double>(), E.as<double>(), F.as<double>(), s);
     } else {
-        launch_trimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), s);
+        launch_trimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), s);
         if (ctx->timing) cudaEventRecord(ctx->evp[2], s);
-        if ((rc = pip_launch(3, X.as<double>(), O.as<double>(), n, ld, s, &err))) return rc;
+        if ((rc = pip_launch(3, X.as<double>(), O.as<double>(), n, ld, s, &err, true))) return rc;
         if (ctx->timing) cudaEventRecord(ctx->evp[3], s);
-        launch_trimer_forces(pos, idx, tuples, first, n, ld, box, X.as<double>(), R.as<double>(), O.as<double>(),
-                             E.as<double>(), F.as<double>(), s);
+        launch_trimer_forces(pos, idx, tuples, first, n, ld, box, O.as<double>(), E.as<double>(), F.as<double>(), s);
     }
     if ((rc = ci.build(tuples, width, first, n, ctx->n_mol, L.cub_tmp, s, err))) return rc;
     launch_force_reduce(ci, width, F.as<double>(), ctx->n_mol, ctx->f_mol.as<double>(), !first_into_fmol, s);
@@ -447,10 +443,10 @@ int mbpol_eval_tuples(int order, const double* pos_nm, int32_t n_mol, const int3
     cudaStream_t s = (cudaStream_t)stream;
     const int nv = order == 2 ? NV2 : NV3;
     const int64_t ld = round_up(n, 32);
-    DeviceBuf X, R, O, I;
+    DeviceBuf X, O, I;
     std::string err;
     int rc;
-    if ((rc = X.reserve(sizeof(double) * nv * ld, err)) || (rc = R.reserve(sizeof(double) * nv * ld, err)) ||
+    if ((rc = X.reserve(sizeof(double) * nv * ld, err)) ||
         (rc = O.reserve(sizeof(double) * (nv + 1) * ld, err)) || (rc = I.reserve(sizeof(int32_t) * 3 * (size_t)n_mol, err)))
         return fail(nullptr, rc, err);
     std::vector<int32_t> idx(3 * (size_t)n_mol);
@@ -460,15 +456,13 @@ int mbpol_eval_tuples(int order, const double* pos_nm, int32_t n_mol, const int3
     for (int d = 0; d < 3; ++d) box.len[d] = box_nm ? box_nm[d] : 0.0;
     box.periodic = periodic ? 1 : 0;
     if (order == 2) {
-        launch_dimer_vars(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), R.as<double>(), s);
-        if ((rc = pip_launch(2, X.as<double>(), O.as<double>(), n, ld, s, &err))) return fail(nullptr, rc, err);
-        launch_dimer_forces(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), R.as<double>(),
-                            O.as<double>(), e_each, f_each, s);
+        launch_dimer_vars(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), s);
+        if ((rc = pip_launch(2, X.as<double>(), O.as<double>(), n, ld, s, &err, true))) return fail(nullptr, rc, err);
+        launch_dimer_forces(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, O.as<double>(), e_each, f_each, s);
     } else {
-        launch_trimer_vars(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), R.as<double>(), s);
-        if ((rc = pip_launch(3, X.as<double>(), O.as<double>(), n, ld, s, &err))) return fail(nullptr, rc, err);
-        launch_trimer_forces(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), R.as<double>(),
-                             O.as<double>(), e_each, f_each, s);
+        launch_trimer_vars(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, X.as<double>(), s);
+        if ((rc = pip_launch(3, X.as<double>(), O.as<double>(), n, ld, s, &err, true))) return fail(nullptr, rc, err);
+        launch_trimer_forces(pos_nm, I.as<int32_t>(), tuples, 0, n, ld, box, O.as<double>(), e_each, f_each, s);
     }
     CKC(cudaStreamSynchronize(s));   // temporaries are freed on return
     CKC(cudaGetLastError());

@@ -32,7 +32,7 @@ struct mbpol_ctx {
     DeviceBuf idx;
     TupleLists lists;
     ContributionIndex ci2, ci3;
-    DeviceBuf x2, r2, o2, e2, f2, x3, r3, o3, e3, f3;
+    DeviceBuf x2, o2, e2, f2, x3, o3, e3, f3;
     DeviceBuf f_mol, e_partial, d_energy, pos_stage, force_stage, e1;
     cudaEvent_t ev[6] = {}, evp[4] = {};      // stage events; events around the two polynomial kernels
     cudaEvent_t evc[4] = {};                  // mbpol_eval_distributed: around the broadcast and the reduce

@@ -49,25 +49,25 @@ struct BoxArg {
     int periodic;
 };
 
-// variables: x[nv][ld] and reciprocal distances rinv[nv][ld] for the post stage
+// variables x[nv][ld] (tuple index fastest)
 void launch_dimer_vars(const double* pos, const int32_t* idx, const int32_t* pairs, int64_t first, int64_t n, int64_t ld,
-                       BoxArg box, double* x, double* rinv, cudaStream_t s);
+                       BoxArg box, double* x, cudaStream_t s);
 void launch_trimer_vars(const double* pos, const int32_t* idx, const int32_t* trips, int64_t first, int64_t n, int64_t ld,
-                        BoxArg box, double* x, double* rinv, cudaStream_t s);
-// chain rule + switch: per-tuple energies e[n] and force blocks f[n][18|27]
+                        BoxArg box, double* x, cudaStream_t s);
+// chain rule + switch from poly[1+nv][ld] = {E, x_i dE/dx_i}: per-tuple energies e[n] and force blocks f[n][18|27]
 void launch_dimer_forces(const double* pos, const int32_t* idx, const int32_t* pairs, int64_t first, int64_t n, int64_t ld,
-                         BoxArg box, const double* x, const double* rinv, const double* poly, double* e, double* f,
-                         cudaStream_t s);
+                         BoxArg box, const double* poly, double* e, double* f, cudaStream_t s);
 void launch_trimer_forces(const double* pos, const int32_t* idx, const int32_t* trips, int64_t first, int64_t n,
-                          int64_t ld, BoxArg box, const double* x, const double* rinv, const double* poly, double* e,
-                          double* f, cudaStream_t s);
+                          int64_t ld, BoxArg box, const double* poly, double* e, double* f, cudaStream_t s);
 
 // ---- one-body term (onebody.cu): molecules [first, first+n), forces added in place, e_mol[n] in kJ/mol ----------------
 void launch_onebody(const double* pos, const int32_t* idx, int first, int n, BoxArg box, double* force, double* e_mol,
                     cudaStream_t s);
 
 // ---- polynomial stage (pip_module.cu): generated PTX kernels loaded through the driver API --------------------------
-int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, cudaStream_t s, std::string* err);
+// out[0][t] = E, out[1 + i][t] = dE/dx_i, or x_i dE/dx_i with scale_by_x (what the force kernels consume)
+int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, cudaStream_t s, std::string* err,
+               bool scale_by_x = false);
 int pip_instruction_count(int order);
 
 }  // namespace mbpol

@@ -91,7 +91,8 @@ int ensure_loaded(int dev, std::string* err) {
 
 int pip_instruction_count(int order) { return order == 2 ? PIP2B_NINSTR : order == 3 ? PIP3B_NINSTR : -1; }
 
-int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, cudaStream_t s, std::string* err) {
+int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, cudaStream_t s, std::string* err,
+               bool scale_by_x) {
     if (order != 2 && order != 3) {
         if (err) *err = "pip order must be 2 or 3";
         return MBPOL_EINVAL;
@@ -113,8 +114,8 @@ int pip_launch(int order, const double* x, double* out, int64_t n, int64_t ld, c
     const unsigned block = order == 2 ? PIP2B_BLOCK : PIP3B_BLOCK, smem = order == 2 ? PIP2B_SMEM : PIP3B_SMEM;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     const int nk = order == 2 ? PIP2B_NKERN : PIP3B_NKERN;
-    for (int k = 0; k < nk; ++k) {      // class kernels: the first overwrites `out`, the others accumulate into it
-        acc = k > 0;
+    for (int k = 0; k < nk; ++k) {      // mode bit 0: accumulate into `out` (unused: one kernel per polynomial),
+        acc = (k > 0 ? 1u : 0u) | (scale_by_x ? 2u : 0u);      // bit 1: rows 1.. = x_i dE/dx_i
         CUresult r = g_api.launchKernel(order == 2 ? g_dev[dev].fn2[k] : g_dev[dev].fn3[k], grid, 1, 1, block, 1, 1, smem,
                                         (CUstream)s, args, nullptr);
         if (r != CUDA_SUCCESS) {

@@ -461,7 +461,11 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                fall_copies=2, group=4):
     """One interpreter kernel
 
-        {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 accumulate)
+        {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 mode)
+
+    mode bit 0: add into `out` instead of overwriting it; bit 1: rows 1.. receive x_i dE/dx_i instead of dE/dx_i (every
+    variable is exp(..) [/ r] of one distance, so its chain rule needs exactly that product: the force kernels then
+    never read x again, csrc/tuples.cu).
 
     One thread per tuple; x / g slots and the adjoints in registers.  The stream is staged through a double-buffered
     shared-memory window: when chunk c starts every thread issues cp.async copies of its 16-byte pieces of chunk c + 1
@@ -490,8 +494,9 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %xkb, %gkb;")
-    w(".reg .pred %valid, %pacc, %pself; .reg .u32 %acc;")
-    w("ld.param.u32 %acc, [p_acc]; setp.ne.u32 %pacc, %acc, 0;")
+    w(".reg .pred %valid, %pacc, %pself, %pscale; .reg .u32 %acc, %accb;")
+    w("ld.param.u32 %acc, [p_acc]; and.b32 %accb, %acc, 1; setp.ne.u32 %pacc, %accb, 0;")
+    w("and.b32 %accb, %acc, 2; setp.ne.u32 %pscale, %accb, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
     w("cvta.to.global.u64 %px, %px; cvta.to.global.u64 %po, %po;")
     w("mov.u32 %r0, %ctaid.x; mov.u32 %r1, %ntid.x; mov.u32 %r2, %tid.x;")
@@ -757,6 +762,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     w("st.global.f64 [%po], %vc; add.u64 %po, %po, %ldb;")
     for i in range(nv):
         w(f"ld.shared.f64 %gk, [%sg+{i * NT * 8}];")
+        w(f"@%pscale ld.shared.f64 %w, [%sx+{i * NT * 8}]; @%pscale mul.rn.f64 %gk, %gk, %w;")
         w("@%pacc ld.global.f64 %w, [%po]; @%pacc add.rn.f64 %gk, %gk, %w;")
         w("st.global.f64 [%po], %gk; add.u64 %po, %po, %ldb;")
     w("DONE:")
