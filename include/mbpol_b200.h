@@ -92,6 +92,14 @@ int  mbpol_update_particles(mbpol_ctx* ctx, int32_t n_molecules, const int32_t* 
 /* rectangular periodic box edge lengths (extractBoxSize, MBPolReferenceKernels.cpp:63-66) */
 int  mbpol_set_box(mbpol_ctx* ctx, const double box_nm[3]);
 
+/* Verlet skin.  0 (default) = neighbour rows are rebuilt from the cell grid on every evaluation, like
+ * the reference (MBPolReferenceKernels.cpp:379-383).  skin_nm > 0: the cell scan builds rows out to (largest cutoff +
+ * skin), keeps them while no oxygen has moved more than skin / 2 (minimum image) since, and every evaluation filters
+ * them with the exact d^2 <= cutoff^2 test at the current positions -- the pair / triplet lists are the reference's sets
+ * at every step either way.  Applies to unpartitioned contexts (world = 1); mbpol_stats.lists_reused / n_row_builds tell
+ * what happened. */
+int  mbpol_set_skin(mbpol_ctx* ctx, double skin_nm);
+
 /* multi-GPU owner-molecule partition: this context evaluates only the tuples whose owner (highest molecule index I)
  * falls in slice `rank` of `world` slices balanced by 30,601*dimers + 111,818*trimers per owner.
  * world = 1 (default) evaluates everything.  Forces / energies returned are then partial sums to be all-reduced.

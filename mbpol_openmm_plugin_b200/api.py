@@ -176,6 +176,10 @@ class _Engine:
         b = (C.c_double * 3)(*[float(x) for x in box])
         _lib.check(self.L.mbpol_set_box(self.h, b), self.h)
 
+    def set_skin(self, skin_nm):
+        """Verlet skin for the neighbour rows (0 = rebuild every evaluation, the reference's behaviour)"""
+        _lib.check(self.L.mbpol_set_skin(self.h, float(skin_nm)), self.h)
+
     def set_partition(self, rank, world):
         _lib.check(self.L.mbpol_set_partition(self.h, rank, world), self.h)
 

@@ -260,6 +260,13 @@ int mbpol_set_box(mbpol_ctx* ctx, const double box_nm[3]) {
     return MBPOL_OK;
 }
 
+int mbpol_set_skin(mbpol_ctx* ctx, double skin_nm) {
+    if (!ctx || !(skin_nm >= 0.0) || !std::isfinite(skin_nm)) return fail(ctx, MBPOL_EINVAL, "mbpol_set_skin: bad argument");
+    ctx->lists.skin = skin_nm;
+    ctx->lists.skin_valid = false;
+    return MBPOL_OK;
+}
+
 int mbpol_set_partition(mbpol_ctx* ctx, int32_t rank, int32_t world) {
     if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(ctx, MBPOL_EINVAL, "mbpol_set_partition: bad rank/world");
     ctx->rank = rank;

@@ -318,6 +318,62 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
     }
 }
 
+// ---- Verlet skin ---------------------------------------------------------------------------------------------------
+// The reference rebuilds its neighbour lists on every call (MBPolReferenceKernels.cpp:379-383).  With a skin s > 0 the
+// cell scan instead produces SUPER rows -- lower-index oxygens within (largest cutoff + s) -- which stay valid while no
+// oxygen has moved farther than s / 2 from where it was when they were built; every evaluation filters them with the
+// exact d2 <= c^2 test at the CURRENT positions, so the pair / triplet lists the polynomial stage consumes are still the
+// reference's sets, bit for bit, at every step.
+
+// flag = 1 if any oxygen moved more than sqrt(limit2) (minimum image) away from its reference position
+__global__ void displacement_kernel(const double* __restrict__ posO, const double* __restrict__ ref, int n, GridArg g,
+                                    double limit2, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d2 = pair_d2(ref + 3 * i, posO + 3 * i, g);
+    if (!(d2 <= limit2)) atomicExch(flag, 1);
+}
+
+// one warp per molecule: keep the entries of its super row that are within the cutoffs NOW (same screened distance test
+// as rows_warp_kernel, evaluated from the higher index); order is preserved, so the rows stay sorted
+__global__ void __launch_bounds__(ROWS_WARPS * 32) filter_rows_kernel(
+    const double* __restrict__ posO, int n, GridArg g, const int* __restrict__ snbr, const int* __restrict__ slow,
+    double c2sq, double c3sq, int* __restrict__ nbr2, int* __restrict__ nbr3, int* __restrict__ low2,
+    int* __restrict__ low3, int64_t* __restrict__ ro2, int64_t* __restrict__ ro3, int* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * ROWS_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const unsigned lt = (1u << lane) - 1u;
+    const int* row = snbr + (size_t)i * ROW_CAP2;
+    const int len = slow[i];
+    int n2 = 0, n3 = 0;
+    for (int k0 = 0; k0 < len; k0 += 32) {
+        const int k = k0 + lane;
+        const int j = k < len ? row[k] : -1;
+        bool p2 = false, p3 = false;
+        if (j >= 0) {
+            const double d2 = screened_d2(posO + 3 * i, posO + 3 * j, g, c2sq, c3sq);
+            p2 = d2 <= c2sq;
+            p3 = d2 <= c3sq;
+        }
+        const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
+        if (p2) nbr2[(size_t)i * ROW_CAP2 + n2 + __popc(b2 & lt)] = j;
+        if (p3) {
+            const int pos = n3 + __popc(b3 & lt);
+            if (pos < ROW_CAP3) nbr3[(size_t)i * ROW_CAP3 + pos] = j;
+        }
+        n2 += __popc(b2);
+        n3 += __popc(b3);
+    }
+    if (lane == 0) {
+        if (n3 > ROW_CAP3) atomicExch(overflow, 1);
+        low2[i] = n2;
+        low3[i] = min(n3, ROW_CAP3);
+        ro2[i] = (int64_t)i * ROW_CAP2;
+        ro3[i] = (int64_t)i * ROW_CAP3;
+    }
+}
+
 // sliced build: flag the 0.45 nm neighbours J < i_lo of the owners [i_lo, i_hi) -- their rows are needed to close the
 // chain triplets (I, J, K in nearby[J]) of this rank's owners
 __global__ void mark_halo_kernel(int i_lo, int i_hi, const int* __restrict__ low3, const int* __restrict__ nbr3,
@@ -495,18 +551,43 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     RES(posO, 3 * n, double);
     gather_oxygens_kernel<<<blocks(n), 128, 0, s>>>(pos, idx, n, posO.as<double>()); MBPOL_COUNT_LAUNCH(1);
 
-    // ---- grid ---------------------------------------------------------------------------------------------------
-    // rows are only needed out to the largest finite cutoff in use; "no cutoff" (1e10) degenerates to one cell
-    const double rc_max = fmax(want2 ? cut2 : 0.0, want3 ? cut3 : 0.0) * (1.0 + 1e-6);
+    // ---- Verlet skin: can the super rows of an earlier build be filtered instead of scanning the cells again? --------
+    const double cmax = fmax(want2 ? cut2 : 0.0, want3 ? cut3 : 0.0);
+    const bool use_skin = skin > 0.0 && !slice && !force_two_pass && cmax < 1e9 &&
+                          (!periodic || (2.0 * (cmax + skin) <= box[0] && 2.0 * (cmax + skin) <= box[1] &&
+                                         2.0 * (cmax + skin) <= box[2]));
     GridArg g;
     g.periodic = periodic ? 1 : 0;
+    for (int d = 0; d < 3; ++d) {
+        g.box[d] = periodic ? box[d] : 0.0;
+        g.inv_box[d] = periodic ? 1.0 / box[d] : 0.0;
+        g.lo[d] = 0.0;
+        g.inv_extent[d] = 0.0;
+        g.nc[d] = 1;
+    }
+    bool reuse_rows = false;
+    if (use_skin && skin_valid && skin_n == n && skin_periodic == periodic && skin_cmax == cmax && skin_built == skin &&
+        skin_want2 == want2 && skin_want3 == want3 &&
+        (!periodic || (skin_box[0] == box[0] && skin_box[1] == box[1] && skin_box[2] == box[2]))) {
+        RES(scratch, 8, int64_t);
+        CK(cudaMemsetAsync(scratch.ptr, 0, sizeof(int), s));
+        displacement_kernel<<<blocks(n), 128, 0, s>>>(posO.as<double>(), pos_ref.as<double>(), n, g, 0.25 * skin * skin,
+                                                     scratch.as<int>()); MBPOL_COUNT_LAUNCH(1);
+        int moved = 1;
+        CK(cudaMemcpyAsync(&moved, scratch.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        reuse_rows = !moved;
+    }
+    if (!use_skin) skin_valid = false;
+    rows_reused = reuse_rows;
+
+    if (!reuse_rows) {
+    // ---- grid ---------------------------------------------------------------------------------------------------
+    // rows are only needed out to the largest finite cutoff in use (+ skin); "no cutoff" (1e10) degenerates to one cell
+    const double rc_max = (cmax + (use_skin ? skin : 0.0)) * (1.0 + 1e-6);
     double extent[3];
     if (periodic) {
-        for (int d = 0; d < 3; ++d) {
-            g.box[d] = box[d];
-            g.lo[d] = 0.0;
-            extent[d] = box[d];
-        }
+        for (int d = 0; d < 3; ++d) extent[d] = box[d];
     } else {
         RES(scratch, 6, double);
         bbox_kernel<<<1, 256, 0, s>>>(posO.as<double>(), n, scratch.as<double>()); MBPOL_COUNT_LAUNCH(1);
@@ -514,7 +595,6 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         CK(cudaMemcpyAsync(bb, scratch.ptr, sizeof bb, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         for (int d = 0; d < 3; ++d) {
-            g.box[d] = 0.0;
             g.lo[d] = bb[d];
             extent[d] = fmax(bb[3 + d] - bb[d], 1e-9) * (1.0 + 1e-9);
         }
@@ -531,10 +611,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         g.nc[d] = (g.nc[d] + 1) / 2;
         ncell *= g.nc[d];
     }
-    for (int d = 0; d < 3; ++d) {
-        g.inv_extent[d] = 1.0 / extent[d];
-        g.inv_box[d] = periodic ? 1.0 / box[d] : 0.0;
-    }
+    for (int d = 0; d < 3; ++d) g.inv_extent[d] = 1.0 / extent[d];
 
     // ---- cells --------------------------------------------------------------------------------------------------
     ++n_row_builds;
@@ -556,6 +633,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
     }
     cell_fill_kernel<<<blocks(n), 128, 0, s>>>(n, cell_of.as<int>(), cell_start.as<int>(), cell_cursor.as<int>(),
                                                cell_members.as<int>()); MBPOL_COUNT_LAUNCH(1);
+    }
 
     // ---- neighbour rows -----------------------------------------------------------------------------------------
     const double c2sq = want2 ? cut2 * cut2 : -1.0, c3sq = want3 ? cut3 * cut3 : -1.0;
@@ -609,11 +687,33 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         CK(cudaMemsetAsync(scratch.ptr, 0, sizeof(int), s));
         CK(cudaMemsetAsync(low2.ptr, 0, sizeof(int) * (n + 1), s));
         CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
+        if (use_skin) {
+            if (!reuse_rows) {                           // super rows out to cmax + skin, positions remembered
+                RES(snbr, (size_t)n * ROW_CAP2 + 1, int);
+                RES(slow, n + 1, int);
+                RES(sk_low3, n + 1, int);
+                RES(sk_ro, 2 * (size_t)(n + 1), int64_t);
+                RES(pos_ref, 3 * n, double);
+                CK(cudaMemsetAsync(slow.ptr, 0, sizeof(int) * (n + 1), s));
+                const double cs = (cmax + skin) * (cmax + skin);
+                rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+                    posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), cs, -1.0, snbr.as<int>(),
+                    nbr3.as<int>(), slow.as<int>(), sk_low3.as<int>(), sk_ro.as<int64_t>(), sk_ro.as<int64_t>() + n + 1,
+                    scratch.as<int>(), 0, n, nullptr);
+                CK(cudaMemcpyAsync(pos_ref.ptr, posO.ptr, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s));
+                MBPOL_COUNT_LAUNCH(1);
+            }
+            filter_rows_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+                posO.as<double>(), n, g, snbr.as<int>(), slow.as<int>(), c2sq, c3sq, nbr2.as<int>(), nbr3.as<int>(),
+                low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(), scratch.as<int>());
+            MBPOL_COUNT_LAUNCH(1);
+        } else {
         rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
             posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), c2sq, c3sq, nbr2.as<int>(),
             nbr3.as<int>(), low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(), scratch.as<int>(),
             slice ? slice_lo : 0, slice ? slice_hi : n, nullptr);
         MBPOL_COUNT_LAUNCH(1);
+        }
         q_count = low3.as<int>();
         if (slice && want3) {
             RES(halo, n + 1, unsigned char);
@@ -633,6 +733,20 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         int overflow = 0;
         if ((rc = pair_offsets(&overflow))) return rc;
         if (overflow) fast = false;                      // some row exceeded the fixed stride: redo with the CSR path
+        if (use_skin) {
+            skin_valid = !overflow;
+            skin_n = n;
+            skin_periodic = periodic;
+            skin_cmax = cmax;
+            skin_built = skin;
+            skin_want2 = want2;
+            skin_want3 = want3;
+            for (int d = 0; d < 3; ++d) skin_box[d] = box[d];
+        }
+    }
+    if (!fast && reuse_rows) {                           // a filtered 3B row overflowed its stride: the general path needs
+        skin_valid = false;                              // the cell grid, which a reused build does not have -> start over
+        return build(pos, idx, n_mol, box, periodic, cut2, cut3, want2, want3, s, err, slice_lo, slice_hi);
     }
     if (!fast) {
         slice = false;                                   // the general CSR path always builds every row

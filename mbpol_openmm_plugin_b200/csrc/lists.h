@@ -47,6 +47,13 @@ struct TupleLists {
     DeviceBuf cell_of, cell_count, cell_start64, cell_start, cell_cursor, cell_members;
     DeviceBuf cnt2, cnt3, ro2, ro3, low2, low3, nbr2, nbr3;
     DeviceBuf pstart, qstart, pairs, qpairs, tcnt, tstart, trips, weight, halo, own3;
+    // Verlet skin (0 = rebuild the rows on every call, the reference's behaviour): super rows + the positions they were
+    // built from, and what they were built for
+    double skin = 0.0;
+    bool skin_valid = false, skin_periodic = false, skin_want2 = false, skin_want3 = false;
+    int skin_n = 0;
+    double skin_cmax = 0.0, skin_built = 0.0, skin_box[3] = {0, 0, 0};
+    DeviceBuf snbr, slow, sk_low3, sk_ro, pos_ref;
 
     int build(const double* pos, const int32_t* idx, int n_mol, const double box[3], bool periodic, double cut2,
               double cut3, bool want2, bool want3, cudaStream_t s, std::string& err, int slice_lo = 0,

@@ -13,7 +13,7 @@
 // exp).  The force kernels therefore read the polynomial output only; x is read once (by the polynomial kernel) and
 // 1/r never touches memory: 1,392 B per trimer through HBM instead of 2,256 B (2B: 1,050 instead of 1,796).
 // The sites live in a shared-memory row per thread during the chain rule, not in registers, and the variables are
-// processed in three batches so that a dozen loads per thread are in flight together without spilling.
+// staged through shared memory with cp.async so that all its loads are in flight at once (see stage_poly).
 //
 // Behaviour follows the Reference platform:
 //   2B  MBPolReferenceTwoBodyForce::calculatePairIxn      platforms/reference/src/MBPolReferenceTwoBodyForce.cpp:110-296
@@ -22,6 +22,8 @@
 //   3B  MBPolReferenceThreeBodyForce::calculateTripletIxn platforms/reference/src/MBPolReferenceThreeBodyForce.cpp:122-293
 //       var / g_var / threebody_f_switch                  platforms/reference/src/MBPolReferenceThreeBodyForce.cpp:67-120
 //   PBC imageParticles / imageMolecules                   platforms/reference/src/MBPolReferenceTwoBodyForce.cpp:66-109
+#include <cuda_pipeline_primitives.h>
+
 #include "internal.h"
 
 namespace mbpol {
@@ -168,6 +170,17 @@ __global__ void __launch_bounds__(128) dimer_vars_kernel(const double* __restric
 #undef V
 }
 
+// The force kernels are latency-bound on the polynomial outputs they read (ncu: 12-14 long-scoreboard stall cycles per
+// issue, DRAM 13 %, 12 warps per SM): every thread therefore issues ALL its 1 + NV loads up front as 8-byte cp.async
+// copies into a shared-memory column block [1 + NV][128] (coalesced across the CTA, no registers held), does its gather /
+// imaging / switching-function work while they fly, and waits once.  Each thread reads back only what it copied itself.
+template <int NVARS>
+__device__ __forceinline__ void stage_poly(const double* __restrict__ poly, int64_t ld, int64_t t, double* col) {
+#pragma unroll
+    for (int i = 0; i <= NVARS; ++i) __pipeline_memcpy_async(col + i * 128, poly + (size_t)i * ld + t, sizeof(double));
+    __pipeline_commit();
+}
+
 // Shared-memory row of one thread: its sites during the chain rule, its force block afterwards.
 template <int NS>
 struct SiteRow {
@@ -186,9 +199,12 @@ __global__ void __launch_bounds__(128, 3) dimer_forces_kernel(const double* __re
                                                               int64_t ld, BoxArg box,
                                                               const double* __restrict__ poly /* E, x_i dE/dx_i */,
                                                               double* __restrict__ e_out, double* __restrict__ f_out) {
-    __shared__ double sh[128 * 30];                     // 10 sites per thread (stride 30 doubles: conflict-free)
+    extern __shared__ double dyn_smem[];
+    double* sh = dyn_smem;                              // [128][30]: 10 sites per thread (stride 30 doubles: conflict-free)
+    double* col = dyn_smem + 128 * 30 + threadIdx.x;    // [1 + NV2][128]: this thread's polynomial outputs
     const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
     const int64_t t = cta_first + threadIdx.x;
+    if (t < n) stage_poly<NV2>(poly, ld, t, col);
     SiteRow<10> row{sh + 30 * threadIdx.x};
     V3 F[10];
 #pragma unroll
@@ -202,8 +218,9 @@ __global__ void __launch_bounds__(128, 3) dimer_forces_kernel(const double* __re
 #pragma unroll
         for (int c = 0; c < 10; ++c) row.put(c, s[c]);
     }
+    __pipeline_wait_prior(0);
     if (active) {
-        const double E_poly = poly[t];
+        const double E_poly = col[0];
         // switching function first: its gradient seeds F[Oa], F[Ob], and every later term carries sw * unit conversion,
         // so that nothing but F stays live across the variable batches
         double gsw;
@@ -220,19 +237,13 @@ __global__ void __launch_bounds__(128, 3) dimer_forces_kernel(const double* __re
     {                                                                                \
         const V3 d = row.get(p) - row.get(q);                                        \
         const double ri = rsqrt(dot(d, d));                                          \
-        const double xg = poly[(size_t)((i) + 1) * ld + t] * scale;                  \
+        const double xg = col[((i) + 1) * 128] * scale;                              \
         const double gg = ((kind) ? -((k) + ri) * ri : -(k) * ri) * xg;              \
         const V3 dg = d * gg;                                                        \
         F[p] += dg;                                                                  \
         F[q] -= dg;                                                                  \
     }
-        // three batches: the loads of a batch (polynomial outputs + site rows) are in flight together, the fence keeps
-        // the compiler from hoisting all 31 at once
-        MBPOL_2B_VARS_A(V)
-        asm volatile("" ::: "memory");
-        MBPOL_2B_VARS_B(V)
-        asm volatile("" ::: "memory");
-        MBPOL_2B_VARS_C(V)
+        MBPOL_2B_VARS(V)
 #undef V
         // monomer::grads: fold the lone-pair gradients back onto O,H,H (mbpol_2body_constants.cpp:76-95); linear in F,
         // so the scale factor folded into gg above passes through
@@ -344,9 +355,12 @@ __global__ void __launch_bounds__(128, 3) trimer_forces_kernel(const double* __r
                                                                int64_t n, int64_t ld, BoxArg box,
                                                                const double* __restrict__ poly /* E, x_i dE/dx_i */,
                                                                double* __restrict__ e_out, double* __restrict__ f_out) {
-    __shared__ double sh[128 * 27];                     // 9 sites per thread, then its 9 x 3 force block
+    extern __shared__ double dyn_smem[];
+    double* sh = dyn_smem;                              // [128][27]: 9 sites per thread, then its 9 x 3 force block
+    double* col = dyn_smem + 128 * 27 + threadIdx.x;    // [1 + NV3][128]: this thread's polynomial outputs
     const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
     const int64_t t = cta_first + threadIdx.x;
+    if (t < n) stage_poly<NV3>(poly, ld, t, col);
     SiteRow<9> row{sh + 27 * threadIdx.x};
     V3 F[9];
 #pragma unroll
@@ -361,6 +375,7 @@ __global__ void __launch_bounds__(128, 3) trimer_forces_kernel(const double* __r
 #pragma unroll
         for (int c = 0; c < 9; ++c) row.put(c, s[c]);
     }
+    __pipeline_wait_prior(0);
     if (active) {
         // switching functions first (MBPolReferenceThreeBodyForce.cpp:106-120, 265-277): their gradient seeds the three
         // oxygens, and only `unit` stays live across the variable batches
@@ -369,7 +384,7 @@ __global__ void __launch_bounds__(128, 3) trimer_forces_kernel(const double* __r
         const double sac = f_switch(dac, R3I, R3F, gac);
         const double sbc = f_switch(dbc, R3I, R3F, gbc);
         const double sw = sab * sac + sab * sbc + sac * sbc;
-        const double E_poly = poly[t];
+        const double E_poly = col[0];
         gab *= (sac + sbc) * E_poly / dab;
         gac *= (sab + sbc) * E_poly / dac;
         gbc *= (sab + sac) * E_poly / dbc;
@@ -384,16 +399,12 @@ __global__ void __launch_bounds__(128, 3) trimer_forces_kernel(const double* __r
     {                                                                                  \
         const V3 d = row.get(p) - row.get(q);                   /* nm */                \
         const double ri = rsqrt(dot(d, d)) * (1.0 / NM_TO_A);   /* 1 / Angstrom */      \
-        const double xg = poly[(size_t)((i) + 1) * ld + t];                            \
+        const double xg = col[((i) + 1) * 128];                                        \
         const V3 dg = d * (-(k) * xg * ri * unit);                                     \
         F[p] += dg;                                                                    \
         F[q] -= dg;                                                                    \
     }
-        MBPOL_3B_VARS_A(V)                              // three batches, see dimer_forces_kernel
-        asm volatile("" ::: "memory");
-        MBPOL_3B_VARS_B(V)
-        asm volatile("" ::: "memory");
-        MBPOL_3B_VARS_C(V)
+        MBPOL_3B_VARS(V)
 #undef V
     }
     if (t < n) e_out[t] = e;
@@ -417,13 +428,19 @@ void launch_trimer_vars(const double* pos, const int32_t* idx, const int32_t* tr
 }
 void launch_dimer_forces(const double* pos, const int32_t* idx, const int32_t* pairs, int64_t first, int64_t n, int64_t ld,
                          BoxArg box, const double* poly, double* e, double* f, cudaStream_t s) {
+    constexpr int smem = sizeof(double) * 128 * (30 + 1 + NV2);
+    static const cudaError_t once = cudaFuncSetAttribute(dimer_forces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    (void)once;
     if (n > 0)
-        dimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, pairs, first, n, ld, box, poly, e, f); MBPOL_COUNT_LAUNCH(1);
+        dimer_forces_kernel<<<grid_for(n, 128), 128, smem, s>>>(pos, idx, pairs, first, n, ld, box, poly, e, f); MBPOL_COUNT_LAUNCH(1);
 }
 void launch_trimer_forces(const double* pos, const int32_t* idx, const int32_t* trips, int64_t first, int64_t n,
                           int64_t ld, BoxArg box, const double* poly, double* e, double* f, cudaStream_t s) {
+    constexpr int smem = sizeof(double) * 128 * (27 + 1 + NV3);
+    static const cudaError_t once = cudaFuncSetAttribute(trimer_forces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    (void)once;
     if (n > 0)
-        trimer_forces_kernel<<<grid_for(n, 128), 128, 0, s>>>(pos, idx, trips, first, n, ld, box, poly, e, f); MBPOL_COUNT_LAUNCH(1);
+        trimer_forces_kernel<<<grid_for(n, 128), 128, smem, s>>>(pos, idx, trips, first, n, ld, box, poly, e, f); MBPOL_COUNT_LAUNCH(1);
 }
 
 }  // namespace mbpol

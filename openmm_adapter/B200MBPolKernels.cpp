@@ -1,9 +1,12 @@
-// See B200MBPolKernels.h.  NOT BUILT here (needs OpenMM); shows exactly which C-ABI call replaces which reference line.
+// See B200MBPolKernels.h.  Which C-ABI call replaces which reference line is noted at every step.
 #include "B200MBPolKernels.h"
 
 #include <map>
 
+#include "CudaPlatform.h"
+#include "openmm/KernelFactory.h"
 #include "openmm/OpenMMException.h"
+#include "openmm/Platform.h"
 #include "openmm/internal/ContextImpl.h"
 
 using namespace MBPolPlugin;
@@ -15,14 +18,10 @@ void check(int rc, mbpol_ctx* ctx) {
     if (rc != MBPOL_OK) throw OpenMMException(mbpol_last_error(ctx));     // error convention of the reference kernels
 }
 
-std::vector<std::vector<int> > particlesOf2B(const MBPolTwoBodyForce& f) {
+template <class Force>
+std::vector<std::vector<int> > particlesOf(const Force& f) {
     std::vector<std::vector<int> > out(f.getNumMolecules());
     for (int i = 0; i < f.getNumMolecules(); ++i) f.getParticleParameters(i, out[i]);   // MBPolReferenceKernels.cpp:345-352
-    return out;
-}
-std::vector<std::vector<int> > particlesOf3B(const MBPolThreeBodyForce& f) {
-    std::vector<std::vector<int> > out(f.getNumMolecules());
-    for (int i = 0; i < f.getNumMolecules(); ++i) f.getParticleParameters(i, out[i]);
     return out;
 }
 
@@ -48,24 +47,40 @@ B200SharedEngine& B200SharedEngine::get(CudaContext& cu) {
     return *e;
 }
 
-void B200SharedEngine::configure2B(const std::vector<std::vector<int> >& particles, double cutoff, int method) {
-    indices.clear();
-    for (const auto& m : particles) indices.insert(indices.end(), m.begin(), m.begin() + 3);
-    cfg.n_molecules = (int)particles.size();
-    cfg.cutoff_2b_nm = cutoff;
-    cfg.method_2b = method;                  // MBPolTwoBodyForce::NonbondedMethod values == MBPOL_* values
-    have2 = true;
+// The engine lives as long as one of the kernels of its context does: a CudaContext address that is reused later
+// must never find a stale engine.
+void B200SharedEngine::release(CudaContext& cu, unsigned flag) {
+    std::map<CudaContext*, B200SharedEngine*>::iterator it = engines.find(&cu);
+    if (it == engines.end()) return;
+    it->second->registered &= ~flag;
+    if (!it->second->registered) {
+        delete it->second;
+        engines.erase(it);
+    }
 }
 
-void B200SharedEngine::configure3B(const std::vector<std::vector<int> >& particles, double cutoff, int method) {
-    if (!have2) {
-        indices.clear();
-        for (const auto& m : particles) indices.insert(indices.end(), m.begin(), m.begin() + 3);
-        cfg.n_molecules = (int)particles.size();
+void B200SharedEngine::configure(unsigned flag, const std::vector<std::vector<int> >& particles, double cutoff, int method,
+                                 int forceGroup) {
+    if (ctx) throw OpenMMException("MBPol B200 kernels: initialize() after the first execute()");
+    std::vector<int32_t> idx;
+    for (size_t m = 0; m < particles.size(); ++m) {
+        if (particles[m].size() < 3) throw OpenMMException("MBPol B200 kernels: each molecule needs the particles {O, H1, H2}");
+        idx.insert(idx.end(), particles[m].begin(), particles[m].begin() + 3);
     }
-    cfg.cutoff_3b_nm = cutoff;
-    cfg.method_3b = method;
-    have3 = true;
+    if (registered && idx != indices)
+        throw OpenMMException("MBPol B200 kernels: MBPolTwoBodyForce and MBPolThreeBodyForce must list the same molecules");
+    indices = idx;
+    cfg.n_molecules = (int)particles.size();
+    if (flag == MBPOL_DO_2B) {
+        cfg.cutoff_2b_nm = cutoff;
+        cfg.method_2b = method;                  // MBPolTwoBodyForce::NonbondedMethod values == MBPOL_* values
+        group2 = forceGroup;
+    } else {
+        cfg.cutoff_3b_nm = cutoff;
+        cfg.method_3b = method;
+        group3 = forceGroup;
+    }
+    registered |= flag;
 }
 
 void B200SharedEngine::ensureCreated(CudaContext& cu) {
@@ -74,81 +89,101 @@ void B200SharedEngine::ensureCreated(CudaContext& cu) {
     cfg.n_particles = cu.getNumAtoms();
     cfg.particle_indices = indices.data();
     cfg.device = cu.getDeviceIndex();
-    if (!have2) { cfg.cutoff_2b_nm = 1e10; cfg.method_2b = MBPOL_CUTOFF_NONPERIODIC; }
-    if (!have3) { cfg.cutoff_3b_nm = 1e10; cfg.method_3b = MBPOL_CUTOFF_NONPERIODIC; }
+    if (!(registered & MBPOL_DO_2B)) { cfg.cutoff_2b_nm = 1e10; cfg.method_2b = MBPOL_CUTOFF_NONPERIODIC; }
+    if (!(registered & MBPOL_DO_3B)) { cfg.cutoff_3b_nm = 1e10; cfg.method_3b = MBPOL_CUTOFF_NONPERIODIC; }
     check(mbpol_create(&ctx, &cfg), nullptr);
-    cudaMalloc(&posBuffer, sizeof(double) * 3 * cu.getNumAtoms());
 }
 
-double B200SharedEngine::execute(CudaContext& cu, unsigned flags) {
+double B200SharedEngine::execute(CudaContext& cu, unsigned flag, int groups) {
     ensureCreated(cu);
     cu.setAsCurrent();
-    // 1. positions: OpenMM's posq (real4, reordered) -> double3 in original atom order.  A 10-line gather kernel
-    //    (posq[atomIndex[i]].xyz -> posBuffer[i], plus posqCorrection in mixed precision) lives in the adapter; the
-    //    1e-9 parity bar needs CudaPrecision=double, which is what the reference's CUDA tests use
-    //    (platforms/cuda/tests/CMakeLists.txt:20-22).
-    gatherPositionsInOriginalOrder(cu, (double*)posBuffer);
-    // 2. box: rectangular only, like extractBoxSize (MBPolReferenceKernels.cpp:63-66)
-    double4 box = cu.getPeriodicBoxSize();
-    double b[3] = {box.x, box.y, box.z};
-    if (cfg.method_2b == MBPOL_CUTOFF_PERIODIC || cfg.method_3b == MBPOL_CUTOFF_PERIODIC) check(mbpol_set_box(ctx, b), ctx);
-    // 3. evaluate on OpenMM's stream; forces stay inside the library ...
-    double e[2];
-    check(mbpol_eval(ctx, (const double*)posBuffer, nullptr, e, flags, cu.getCurrentStream()), ctx);
-    // 4. ... and are added to OpenMM's int64 fixed-point force buffer (value * 2^32, SoA, padded).  The adapter passes
-    //    the atom-order permutation by calling mbpol_update_particles with reordered indices after each reorder.
-    check(mbpol_add_forces_fixed_point(ctx, (long long*)cu.getForce().getDevicePointer(), cu.getPaddedNumAtoms(),
-                                       cu.getCurrentStream()), ctx);
-    return ((flags & MBPOL_DO_2B) ? e[0] : 0.0) + ((flags & MBPOL_DO_3B) ? e[1] : 0.0);
+    // One pass per force evaluation.  The first of our kernels that OpenMM executes in evaluation number
+    // cu.getComputeForceCount() evaluates every registered term whose force group is part of this evaluation; the other
+    // kernel's execute() then has nothing left to do.  (Two separate passes would gather posq and build the tuple lists
+    // twice per step.)
+    const int now = cu.getComputeForceCount();
+    if (now != epoch) {
+        epoch = now;
+        doneThisEpoch = 0;
+    }
+    if (doneThisEpoch & flag) {
+        doneThisEpoch &= ~flag;
+        return 0.0;
+    }
+    unsigned flags = flag;
+    const unsigned other = flag == MBPOL_DO_2B ? MBPOL_DO_3B : MBPOL_DO_2B;
+    const int otherGroup = other == MBPOL_DO_2B ? group2 : group3;
+    if ((registered & other) && (groups & (1 << otherGroup))) flags |= other;
+    // box: rectangular only, like extractBoxSize (MBPolReferenceKernels.cpp:63-66)
+    if (cfg.method_2b == MBPOL_CUTOFF_PERIODIC || cfg.method_3b == MBPOL_CUTOFF_PERIODIC) {
+        const double4 box = cu.getPeriodicBoxSize();
+        const double b[3] = {box.x, box.y, box.z};
+        check(mbpol_set_box(ctx, b), ctx);
+    }
+    // posq (reordered, real4 / double4) -> original-order double3 -> lists + 2B + 3B -> int64 fixed-point force buffer and
+    // energy buffer, all on OpenMM's stream, nothing copied to the host (CudaMBPolKernels.cpp:278-304, 1976-2005)
+    check(mbpol_eval_openmm(ctx, cu.getPosq().getDevicePointer(), cu.getUseDoublePrecision() ? 1 : 0,
+                            (const int32_t*)cu.getAtomIndexArray().getDevicePointer(), cu.getNumAtoms(),
+                            (long long*)cu.getForce().getDevicePointer(), cu.getPaddedNumAtoms(),
+                            cu.getEnergyBuffer().getDevicePointer(),
+                            (cu.getUseDoublePrecision() || cu.getUseMixedPrecision()) ? 1 : 0, flags,
+                            (void*)cu.getCurrentStream()),
+          ctx);
+    mbpol_get_stats(ctx, &stats);
+    ++numEvaluations;
+    doneThisEpoch = flags & ~flag;               // terms evaluated on behalf of the other kernel
+    return 0.0;
 }
 
-void B200SharedEngine::updateParticles(const std::vector<std::vector<int> >& particles) {
+void B200SharedEngine::updateParticles(unsigned flag, const std::vector<std::vector<int> >& particles) {
     std::vector<int32_t> idx;
-    for (const auto& m : particles) idx.insert(idx.end(), m.begin(), m.begin() + 3);
-    check(mbpol_update_particles(ctx, (int)particles.size(), idx.data()), ctx);   // MBPOL_ECHANGED -> "number of particles has changed"
+    for (size_t m = 0; m < particles.size(); ++m) idx.insert(idx.end(), particles[m].begin(), particles[m].begin() + 3);
+    indices = idx;
+    if (ctx) check(mbpol_update_particles(ctx, (int)particles.size(), idx.data()), ctx);   // MBPOL_ECHANGED -> "number of particles has changed"
 }
 
-B200SharedEngine::~B200SharedEngine() {
-    if (posBuffer) cudaFree(posBuffer);
-    mbpol_destroy(ctx);
-}
+B200SharedEngine::~B200SharedEngine() { mbpol_destroy(ctx); }
 
 // ---- CalcMBPolTwoBodyForceKernel ------------------------------------------------------------------------------------
+B200CalcMBPolTwoBodyForceKernel::~B200CalcMBPolTwoBodyForceKernel() { B200SharedEngine::release(cu, MBPOL_DO_2B); }
 void B200CalcMBPolTwoBodyForceKernel::initialize(const System& system, const MBPolTwoBodyForce& force) {
     numMolecules = force.getNumMolecules();
-    std::vector<std::vector<int> > p = particlesOf2B(force);
-    B200SharedEngine::get(cu).configure2B(p, force.getCutoff(), (int)force.getNonbondedMethod());
+    std::vector<std::vector<int> > p = particlesOf(force);
+    B200SharedEngine::get(cu).configure(MBPOL_DO_2B, p, force.getCutoff(), (int)force.getNonbondedMethod(), force.getForceGroup());
     cu.addForce(new MoleculeGroups(p));
 }
 double B200CalcMBPolTwoBodyForceKernel::execute(ContextImpl& context, bool includeForces, bool includeEnergy) {
-    return B200SharedEngine::get(cu).execute(cu, MBPOL_DO_2B);
+    return B200SharedEngine::get(cu).execute(cu, MBPOL_DO_2B, context.getLastForceGroups());
 }
 void B200CalcMBPolTwoBodyForceKernel::copyParametersToContext(ContextImpl& context, const MBPolTwoBodyForce& force) {
     if (numMolecules != force.getNumParticles())
         throw OpenMMException("updateParametersInContext: The number of particles has changed");
-    B200SharedEngine::get(cu).updateParticles(particlesOf2B(force));
+    B200SharedEngine::get(cu).updateParticles(MBPOL_DO_2B, particlesOf(force));
 }
 
 // ---- CalcMBPolThreeBodyForceKernel ----------------------------------------------------------------------------------
+B200CalcMBPolThreeBodyForceKernel::~B200CalcMBPolThreeBodyForceKernel() { B200SharedEngine::release(cu, MBPOL_DO_3B); }
 void B200CalcMBPolThreeBodyForceKernel::initialize(const System& system, const MBPolThreeBodyForce& force) {
     numMolecules = force.getNumMolecules();
-    std::vector<std::vector<int> > p = particlesOf3B(force);
-    B200SharedEngine::get(cu).configure3B(p, force.getCutoff(), (int)force.getNonbondedMethod());
+    std::vector<std::vector<int> > p = particlesOf(force);
+    B200SharedEngine::get(cu).configure(MBPOL_DO_3B, p, force.getCutoff(), (int)force.getNonbondedMethod(), force.getForceGroup());
     cu.addForce(new MoleculeGroups(p));
 }
 double B200CalcMBPolThreeBodyForceKernel::execute(ContextImpl& context, bool includeForces, bool includeEnergy) {
-    return B200SharedEngine::get(cu).execute(cu, MBPOL_DO_3B);
+    return B200SharedEngine::get(cu).execute(cu, MBPOL_DO_3B, context.getLastForceGroups());
 }
 void B200CalcMBPolThreeBodyForceKernel::copyParametersToContext(ContextImpl& context, const MBPolThreeBodyForce& force) {
     if (numMolecules != force.getNumParticles())
         throw OpenMMException("updateParametersInContext: The number of particles has changed");
-    B200SharedEngine::get(cu).updateParticles(particlesOf3B(force));
+    B200SharedEngine::get(cu).updateParticles(MBPOL_DO_3B, particlesOf(force));
 }
 
 // ---- plugin entry points, same names as platforms/cuda/src/CudaMBPolKernelFactory.cpp:43-69 -------------------------
 class B200MBPolKernelFactory : public KernelFactory {
 public:
     KernelImpl* createKernelImpl(std::string name, const Platform& platform, ContextImpl& context) const {
+        // like the reference, contexts[0] drives the whole evaluation (CudaMBPolKernelFactory.cpp:72); several GPUs are
+        // used INSIDE the library (mbpol_comm_*), not through OpenMM's per-context force split
         CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getPlatformData())->contexts[0];
         if (name == CalcMBPolTwoBodyForceKernel::Name())
             return new B200CalcMBPolTwoBodyForceKernel(name, platform, cu, context.getSystem());

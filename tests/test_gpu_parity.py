@@ -589,3 +589,37 @@ def test_full_size_262144_properties(checker):
     _, f3s = eval_parallel(checker, 3, shifted.reshape(-1, 3), idx, trips[touch3], box, True)
     rows = (3 * moved[:, None] + np.arange(3)).ravel()
     assert np.abs(f_s[rows] - (f2s + f3s)[rows]).max() < F_ATOL
+
+
+def test_verlet_skin_lists_equal_the_rebuilt_lists_at_every_step():
+    """mbpol_set_skin: neighbour rows built out to cutoff + skin are kept while no oxygen moved more than skin / 2 and
+    filtered with the exact distance test at every evaluation -> the tuple lists (hence energies and forces) must be
+    IDENTICAL to those of a context that rebuilds everything on every call, at every step of a random walk; a large
+    displacement must trigger a rebuild."""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    a, b = make_context(n, box, True), make_context(n, box, True)
+    b.engine.set_skin(0.1)
+    rng = np.random.default_rng(3)
+    p = pos.reshape(-1, 3).copy()
+    reused = 0
+    for step in range(12):
+        if step == 8:
+            p[rng.choice(len(p) // 3) * 3:][:3] += 0.3               # one molecule jumps 0.3 nm: beyond skin / 2
+        elif step:
+            p += np.repeat(rng.normal(scale=0.004, size=(n, 3)), 3, axis=0)      # rigid per-molecule moves, 0.004 nm rms
+        t = torch.as_tensor(p).cuda()
+        a.setPositions(t)
+        b.setPositions(t)
+        ea, eb = a.getPotentialEnergy(), b.getPotentialEnergy()
+        assert np.array_equal(a.getPairs(), b.getPairs()) and np.array_equal(a.getTriplets(), b.getTriplets())
+        assert ea == eb and torch.equal(a.getForces(), b.getForces())            # same lists, same kernels: bitwise
+        st = b.engine.stats()
+        reused += st["lists_reused"]
+        if step == 8:
+            assert not st["lists_reused"]
+    sa, sb = a.engine.stats(), b.engine.stats()
+    assert sa["n_row_builds"] == 12 and not sa["lists_reused"]
+    assert reused >= 8 and sb["n_row_builds"] <= 4

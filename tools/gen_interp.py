@@ -458,7 +458,7 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
 
 
 def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_blocks=1, piece=64, fall=(), npre=8,
-               fall_copies=2, group=4):
+               fall_copies=2, group=4, maxnreg=0):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 mode)
@@ -488,9 +488,12 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     w = out.append
     w(f".visible .entry {entry}(.param .u64 p_x, .param .u64 p_out, .param .u32 p_n, .param .u32 p_ld, .param .u32 p_acc)")
     w(f".maxntid {NT}, 1, 1")
-    w(f".minnctapersm {min_blocks}")
+    # A register cap below what the program would take makes ptxas keep the pre-loaded payload words -- warp-uniform
+    # values that are live across the indirect branch -- in UNIFORM registers (one R2UR per 32 bits after the load): the
+    # FMAs that consume them then read two vector operands instead of three and issue every second cycle, not every third.
+    w(f".maxnreg {maxnreg}" if maxnreg else f".minnctapersm {min_blocks}")
     w("{")
-    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<72>, %vc, %vd, %ac, %w, %gk, %one, %u0, %u1, %u2, %u3, %a0, %a1, %xk0, %n<16>;")
+    w(f".reg .f64 %x<{nv}>, %g<{nv}>, %c<72>, %vc, %vd, %ac, %w, %gk, %one, %u0, %u1, %u2, %u3, %a0, %a1, %xk0, %n<24>;")
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %xkb, %gkb;")
@@ -621,19 +624,27 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         acc, adj = (["%u0", "%u1"], "%a0") if fused else (["%vc", "%vd"], "%ac")
         started = set() if fused else {"%vc", "%vd"}
         vops, gops = [], []
-        for i, j in enumerate(slots):
+        const0 = None                                        # the node constant starts chain %u0 as the addend of its
+        for i, j in enumerate(slots):                        # first FMA (no register move)
             c = coef(i)
             if j is None:
-                vops.append(f"mov.f64 %u0, {c};")
-                started.add("%u0")
+                const0 = c
+                vops.append(None)
                 continue
             a = acc[i % 2]
             if a in started:
                 vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
+            elif a == "%u0" and const0 is not None:
+                vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {const0};")
+                started.add(a)
+                const0 = None
             else:
                 vops.append(f"mul.rn.f64 {a}, {c}, %x{j};")
                 started.add(a)
             gops.append(f"fma.rn.f64 %g{j}, {c}, {adj}, %g{j};")
+        if const0 is not None:                               # (a fused node with a single slot: chain %u0 never started)
+            vops[0] = f"mov.f64 %u0, {const0};"
+            started.add("%u0")
         if fused:
             w("mul.rn.f64 %a0, %ac, %xk0;")
         done = 0
@@ -641,7 +652,8 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         for q in range(0, n, group):
             cnt = min(group, n - q)
             for u in range(cnt):
-                w(vops[q + u])
+                if vops[q + u] is not None:
+                    w(vops[q + u])
             for u in range(cnt):
                 if slots[q + u] is not None:
                     w(gops[gi])
@@ -676,10 +688,14 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         w(f"mad.lo.u32 %addrb, %kb, {NT * 8}, %sg; ld.shared.f64 %gkb, [%addrb];")
         for i in range(NPRE, nw, 2):
             w(f"ld.shared.v2.f64 {{{coef(i)}, {coef(i + 1)}}}, [%sp+{8 + 8 * i}];")
-        w("mov.f64 %u0, %n0; mov.f64 %u2, %n1;")
         w("mul.rn.f64 %a0, %ac, %xk0;")
         w("mul.rn.f64 %a1, %ac, %xkb;")
-        started = {"%u0", "%u2"}
+        started = set()
+        pending = {"%u0": "%n0", "%u2": "%n1"}               # node constants: addends of the first FMA of their chains
+        if n < 2:                                            # (chains %u0 / %u2 get no FMA: plain moves, before %n0 / %n1
+            w("mov.f64 %u0, %n0; mov.f64 %u2, %n1;")         #  are refilled with the next record's words)
+            started |= {"%u0", "%u2"}
+            pending = {}
         done = 0
         for q in range(0, n, group):
             js = list(range(q, min(q + group, n)))
@@ -688,6 +704,9 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                     a, c = accs[(j + 1) % 2], coef(2 + 2 * j + s)
                     if a in started:
                         w(f"fma.rn.f64 {a}, {c}, %x{m[j]}, {a};")
+                    elif a in pending:
+                        w(f"fma.rn.f64 {a}, {c}, %x{m[j]}, {pending.pop(a)};")
+                        started.add(a)
                     else:
                         w(f"mul.rn.f64 {a}, {c}, %x{m[j]};")
                         started.add(a)
@@ -700,6 +719,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                 w(f"ld.shared.v2.f64 {{%n{done}, %n{done + 1}}}, [%sp+{8 * nwords + 8 + 8 * done}];")
                 done += 2
         preload(8 * nwords, done)
+        assert not pending
         if "%u1" in started:
             w("add.rn.f64 %u0, %u0, %u1;")
         if "%u3" in started:
@@ -809,7 +829,7 @@ def count_fp64(recs, masks, phases, dual):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_weight=40, fall=4, npre=8, fall_copies=2,
-             dual_max=0, group=4):
+             dual_max=0, group=4, maxnreg=0):
     """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual)."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
@@ -831,7 +851,7 @@ def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_
     lines.append("};")
     entry = f"{name}_eval"
     kl, smem = kernel_ptx(name, entry, symbol, masks, nv, phases, dual, block, min_blocks, piece, fall_ops, npre,
-                          fall_copies, group)
+                          fall_copies, group, maxnreg)
     lines += [""] + kl
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
@@ -856,6 +876,7 @@ def main():
         ap.add_argument(f"--sym{two}", type=int, default=d[2], help="size of the leaf-handler library")
         ap.add_argument(f"--npre{two}", type=int, default=d[3], help="payload words of the next record every handler pre-loads")
         ap.add_argument(f"--dual{two}", type=int, default=d[4], help="DUAL records for handlers of at most N slots")
+        ap.add_argument(f"--maxnreg{two}", type=int, default=0, help="register cap (0: none); see kernel_ptx")
     ap.add_argument("--skeleton-weight", type=int, default=40)
     ap.add_argument("--fall", type=int, default=4, help="duplicate leaf handlers that follow themselves at least N times")
     ap.add_argument("--fall-copies", type=int, default=2)
@@ -868,7 +889,7 @@ def main():
         t = "2" if name == "pip2b" else ""
         meta, *_ = generate(name, args.out, getattr(args, "block" + t), args.min_blocks, getattr(args, "piece" + t),
                             getattr(args, "sym" + t), args.skeleton_weight, args.fall, getattr(args, "npre" + t),
-                            args.fall_copies, getattr(args, "dual" + t), args.group)
+                            args.fall_copies, getattr(args, "dual" + t), args.group, getattr(args, "maxnreg" + t))
         print({k: v for k, v in meta.items() if k != "phases"})
 
 
