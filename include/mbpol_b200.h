@@ -191,6 +191,29 @@ int  mbpol_comm_destroy(mbpol_ctx* ctx);
 int  mbpol_eval_distributed(mbpol_ctx* ctx, double* pos_nm, double* force, double* energy, uint32_t flags,
                             void* stream);
 
+/* ---- on-device NVE integrator -------------------------------------------------------------------
+ * n_steps of velocity Verlet around the forces of this context, entirely on the device:
+ *     v += dt/2 F/m ;  x += dt v ;  M sites placed ;  F = F_1B + F_2B + F_3B (x) ;  v += dt/2 F/m
+ * (dt 0.2 fs and the masses of python/example_ini/mbpol_bulk_nve.ini:11 / python/mbpol.xml:3-4 are the caller's choice).
+ *   pos, vel   : DEVICE n_particles x 3, updated in place (nm, nm/ps)
+ *   mass       : DEVICE n_particles (amu); 0 = massless (virtual site): neither kicked nor drifted
+ *   cfg->msite_index : HOST n_molecules particle indices of the molecules' M sites (-1: none) or NULL; placed after every
+ *                drift with the average3 weights cfg->msite_weights (python/mbpol.xml:14: 0.573293118, 0.213353441 x 2)
+ *   energy_log : HOST (n_steps + 1) x 2 doubles {E_pot, E_kin} in kJ/mol (row 0 = start), copied once at the end; NULL =
+ *                no synchronisation at all
+ * No positions, forces or energies cross the host boundary during the run; the tuple lists are rebuilt (or, with
+ * mbpol_set_skin, filtered) every step like the reference does. */
+#define MBPOL_NVE_ONEBODY 64u     /* cfg->flags: include the one-body term (mbpol_eval_onebody) */
+typedef struct mbpol_nve_config {
+    double         dt_ps;
+    uint32_t       flags;             /* MBPOL_DO_2B | MBPOL_DO_3B | MBPOL_NVE_ONEBODY */
+    int32_t        onebody_periodic;  /* MBPolOneBodyForce::Periodic */
+    const int32_t* msite_index;
+    double         msite_weights[3];
+} mbpol_nve_config;
+int  mbpol_nve_run(mbpol_ctx* ctx, double* pos, double* vel, const double* mass, const mbpol_nve_config* cfg,
+                   int32_t n_steps, double* energy_log, void* stream);
+
 /* ---- lower-level entry points used by the unit tests and the roofline benchmark ------------------------------- */
 
 /* evaluate the bare PIP (poly_2b_v6x_eval: poly-2b-v6x.cpp:3 / poly_3b_v2x::eval: poly-3b-v2x.cpp:3) on n tuples.

@@ -226,13 +226,16 @@ __global__ void row_fill_kernel(const double* __restrict__ posO, int n, GridArg 
 // written to fixed-stride rows (ROW_CAP2 / ROW_CAP3 entries).  A row that does not fit raises `overflow` and the caller
 // falls back to the two-pass CSR path above -- same lists either way.
 constexpr int ROW_CAP2 = 64, ROW_CAP3 = 32, ROWS_WARPS = 8;
+constexpr int SKIN_CAP = 128;          // super rows (cutoff + skin): up to ~59 lower-index neighbours at 0.75 nm in liquid water
 
+
+template <int CAP2>
 __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
     const double* __restrict__ posO, int n, GridArg g, const int* __restrict__ cell_start,
     const int* __restrict__ cell_members, double c2sq, double c3sq, int* __restrict__ nbr2, int* __restrict__ nbr3,
     int* __restrict__ low2, int* __restrict__ low3, int64_t* __restrict__ ro2, int64_t* __restrict__ ro3,
     int* __restrict__ overflow, int i_lo, int i_hi, const unsigned char* __restrict__ halo) {
-    __shared__ int s2[ROWS_WARPS][ROW_CAP2], s3[ROWS_WARPS][ROW_CAP3];
+    __shared__ int s2[ROWS_WARPS][CAP2], s3[ROWS_WARPS][ROW_CAP3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * ROWS_WARPS + warp;
     if (w >= n) return;
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
             const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
             if (p2) {
                 const int pos = n2 + __popc(b2 & lt);
-                if (pos < ROW_CAP2) s2[warp][pos] = j;
+                if (pos < CAP2) s2[warp][pos] = j;
             }
             if (p3) {
                 const int pos = n3 + __popc(b3 & lt);
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
             }
         }
     }
-    if (n2 > ROW_CAP2 || n3 > ROW_CAP3) {
+    if (n2 > CAP2 || n3 > ROW_CAP3) {
         if (lane == 0) atomicExch(overflow, 1);
         return;
     }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
         const int v = s2[warp][e];
         int r = 0;
         for (int t = 0; t < n2; ++t) r += s2[warp][t] < v;
-        nbr2[(size_t)i * ROW_CAP2 + r] = v;
+        nbr2[(size_t)i * CAP2 + r] = v;
     }
     for (int e = lane; e < n3; e += 32) {
         const int v = s3[warp][e];
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) rows_warp_kernel(
     if (lane == 0) {
         low2[i] = n2;
         low3[i] = n3;
-        ro2[i] = (int64_t)i * ROW_CAP2;
+        ro2[i] = (int64_t)i * CAP2;
         ro3[i] = (int64_t)i * ROW_CAP3;
     }
 }
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) filter_rows_kernel(
     const int i = blockIdx.x * ROWS_WARPS + (threadIdx.x >> 5);
     if (i >= n) return;
     const unsigned lt = (1u << lane) - 1u;
-    const int* row = snbr + (size_t)i * ROW_CAP2;
+    const int* row = snbr + (size_t)i * SKIN_CAP;
     const int len = slow[i];
     int n2 = 0, n3 = 0;
     for (int k0 = 0; k0 < len; k0 += 32) {
@@ -357,7 +360,10 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) filter_rows_kernel(
             p3 = d2 <= c3sq;
         }
         const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
-        if (p2) nbr2[(size_t)i * ROW_CAP2 + n2 + __popc(b2 & lt)] = j;
+        if (p2) {
+            const int pos = n2 + __popc(b2 & lt);
+            if (pos < ROW_CAP2) nbr2[(size_t)i * ROW_CAP2 + pos] = j;
+        }
         if (p3) {
             const int pos = n3 + __popc(b3 & lt);
             if (pos < ROW_CAP3) nbr3[(size_t)i * ROW_CAP3 + pos] = j;
@@ -366,8 +372,8 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) filter_rows_kernel(
         n3 += __popc(b3);
     }
     if (lane == 0) {
-        if (n3 > ROW_CAP3) atomicExch(overflow, 1);
-        low2[i] = n2;
+        if (n2 > ROW_CAP2 || n3 > ROW_CAP3) atomicExch(overflow, 1);
+        low2[i] = min(n2, ROW_CAP2);
         low3[i] = min(n3, ROW_CAP3);
         ro2[i] = (int64_t)i * ROW_CAP2;
         ro3[i] = (int64_t)i * ROW_CAP3;
@@ -689,14 +695,14 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
         CK(cudaMemsetAsync(low3.ptr, 0, sizeof(int) * (n + 1), s));
         if (use_skin) {
             if (!reuse_rows) {                           // super rows out to cmax + skin, positions remembered
-                RES(snbr, (size_t)n * ROW_CAP2 + 1, int);
+                RES(snbr, (size_t)n * SKIN_CAP + 1, int);
                 RES(slow, n + 1, int);
                 RES(sk_low3, n + 1, int);
                 RES(sk_ro, 2 * (size_t)(n + 1), int64_t);
                 RES(pos_ref, 3 * n, double);
                 CK(cudaMemsetAsync(slow.ptr, 0, sizeof(int) * (n + 1), s));
                 const double cs = (cmax + skin) * (cmax + skin);
-                rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+                rows_warp_kernel<SKIN_CAP><<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
                     posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), cs, -1.0, snbr.as<int>(),
                     nbr3.as<int>(), slow.as<int>(), sk_low3.as<int>(), sk_ro.as<int64_t>(), sk_ro.as<int64_t>() + n + 1,
                     scratch.as<int>(), 0, n, nullptr);
@@ -708,7 +714,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
                 low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(), scratch.as<int>());
             MBPOL_COUNT_LAUNCH(1);
         } else {
-        rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+        rows_warp_kernel<ROW_CAP2><<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
             posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), c2sq, c3sq, nbr2.as<int>(),
             nbr3.as<int>(), low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(), scratch.as<int>(),
             slice ? slice_lo : 0, slice ? slice_hi : n, nullptr);
@@ -722,7 +728,7 @@ int TupleLists::build(const double* pos, const int32_t* idx, int n_mol, const do
             if (slice_hi > slice_lo)                     // (an empty owner range has no halo)
                 mark_halo_kernel<<<blocks(slice_hi - slice_lo), 128, 0, s>>>(slice_lo, slice_hi, low3.as<int>(),
                                                                              nbr3.as<int>(), halo.as<unsigned char>());
-            rows_warp_kernel<<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
+            rows_warp_kernel<ROW_CAP2><<<blocks(n, ROWS_WARPS), ROWS_WARPS * 32, 0, s>>>(
                 posO.as<double>(), n, g, cell_start.as<int>(), cell_members.as<int>(), -1.0, c3sq, nbr2.as<int>(),
                 nbr3.as<int>(), low2.as<int>(), low3.as<int>(), ro2.as<int64_t>(), ro3.as<int64_t>(),
                 scratch.as<int>(), slice_lo, slice_hi, halo.as<unsigned char>());
