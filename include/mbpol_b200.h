@@ -149,7 +149,8 @@ int  mbpol_set_timing(mbpol_ctx* ctx, int32_t enabled);   /* record per-stage CU
 
 /* ---- energies without a host synchronisation -------------------------------------------------------------------
  * mbpol_eval with energy == NULL leaves {E_2B, E_3B} of the call in device memory.  mbpol_energy_device returns that
- * DEVICE pointer (3 doubles: E_2B, E_3B, E_1B of the last evaluations; valid in stream order after the call);
+ * DEVICE pointer (4 doubles: E_2B, E_3B, E_1B, E_dispersion of the last evaluations; valid in stream order after the
+ * call);
  * mbpol_get_energy copies them to the host (synchronises `stream`). */
 const double* mbpol_energy_device(const mbpol_ctx* ctx);
 int  mbpol_get_energy(mbpol_ctx* ctx, double energy[3], void* stream);
@@ -190,6 +191,19 @@ int  mbpol_comm_destroy(mbpol_ctx* ctx);
 #define MBPOL_DIST_NO_BCAST  32u
 int  mbpol_eval_distributed(mbpol_ctx* ctx, double* pos_nm, double* force, double* energy, uint32_t flags,
                             void* stream);
+
+/* ---- TT-damped C6 dispersion ------------------------------------------------------------------
+ * What python/mbpol.xml:37-108 builds as an OpenMM CustomNonbondedForce: for every pair of O / H atoms of DIFFERENT
+ * molecules (M sites excluded) with minimum-image distance r <= cutoff_nm:  E = -C6 tt6(r) / r^6,
+ * tt6 = 1 - exp(-d6 r) sum_{k=0..6} (d6 r)^k / k!, C6 / d6 per atom-class pair (mbpol.xml:53-82); no switching function,
+ * no long-range correction.  The molecules are the context's particle_indices; pos_nm / force DEVICE pointers as in
+ * mbpol_eval (forces are ADDED), energy HOST pointer to 1 double (kJ/mol) or NULL; periodic uses the box of mbpol_set_box
+ * (MBPOL_EBOX if cutoff_nm > box / 2, OpenMM's own rule); cutoff_nm >= 1e9 means no cutoff.  With a partition
+ * (mbpol_set_partition) the rank evaluates the molecule pairs of its owner range. */
+int  mbpol_eval_dispersion(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, double cutoff_nm,
+                           int32_t periodic, void* stream);
+int  mbpol_eval_dispersion_host(mbpol_ctx* ctx, const double* pos_nm, double* force, double* energy, double cutoff_nm,
+                                int32_t periodic);
 
 /* ---- on-device NVE integrator -------------------------------------------------------------------
  * n_steps of velocity Verlet around the forces of this context, entirely on the device:

@@ -26,7 +26,7 @@ EXPORTS = (
     "mbpol_get_triplets", "mbpol_get_stats", "mbpol_set_timing", "mbpol_pip_eval", "mbpol_eval_tuples",
     "mbpol_measure_fp64_peak", "mbpol_pip_instruction_count", "mbpol_eval_onebody", "mbpol_eval_onebody_host",
     "mbpol_energy_device", "mbpol_get_energy", "mbpol_eval_openmm", "mbpol_comm_unique_id", "mbpol_comm_init_rank",
-    "mbpol_comm_adopt", "mbpol_comm_destroy", "mbpol_eval_distributed", "mbpol_set_skin", "mbpol_nve_run",
+    "mbpol_comm_adopt", "mbpol_comm_destroy", "mbpol_eval_distributed", "mbpol_set_skin", "mbpol_nve_run", "mbpol_eval_dispersion", "mbpol_eval_dispersion_host",
 )
 
 
@@ -82,6 +82,8 @@ def load():
     L.mbpol_set_box.argtypes = [vp, C.POINTER(C.c_double)]
     L.mbpol_set_partition.argtypes = [vp, C.c_int32, C.c_int32]
     L.mbpol_set_skin.argtypes = [vp, C.c_double]
+    L.mbpol_eval_dispersion.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_double, C.c_int32, vp]
+    L.mbpol_eval_dispersion_host.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_double, C.c_int32]
     L.mbpol_nve_run.argtypes = [vp, dp, dp, dp, C.POINTER(NveConfig), C.c_int32, dp, vp]
     L.mbpol_eval.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32, vp]
     L.mbpol_eval_host.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32]

@@ -148,7 +148,60 @@ class MBPolOneBodyForce:
         return np.asarray(self._bodies, dtype=np.int32).reshape(-1, 3)
 
 
-DO_1B = 0x100      # host-side selector only: the one-body term has its own C-ABI entry (mbpol_eval_onebody)
+class CustomDispersionForce:
+    """The OpenMM CustomNonbondedForce that python/mbpol.xml:37-108 builds for MB-pol's TT-damped C6 dispersion
+    (-C6 tt6(r) / r^6 between O / H atoms of different molecules, M sites excluded; tables mbpol.xml:53-82), as a
+    parameter object: nonbonded method, cutoff distance (on the atom-atom distance) and one {O, H1, H2} entry per water."""
+
+    NoCutoff = 0
+    CutoffNonPeriodic = 1
+    CutoffPeriodic = 2
+
+    def __init__(self):
+        self._method = self.NoCutoff
+        self._cutoff = 1.0                          # CustomNonbondedForce default cutoff distance, nm
+        self._molecules = []
+        self._group = 0
+
+    def addMolecule(self, particleIndices):
+        p = [int(i) for i in particleIndices]
+        if len(p) < 3:
+            raise MBPolError(_lib.EINVAL, "addMolecule: the particle indices {O, H1, H2} are required")
+        self._molecules.append(p[:3])
+        return len(self._molecules) - 1
+
+    def getNumMolecules(self):
+        return len(self._molecules)
+
+    def getNumParticles(self):
+        return len(self._molecules)
+
+    def getNonbondedMethod(self):
+        return self._method
+
+    def setNonbondedMethod(self, method):
+        if method not in (0, 1, 2):
+            raise MBPolError(_lib.EINVAL, "CustomNonbondedForce: Illegal value for nonbonded method")
+        self._method = int(method)
+
+    def getCutoffDistance(self):
+        return self._cutoff
+
+    def setCutoffDistance(self, distance):
+        self._cutoff = float(distance)
+
+    def getForceGroup(self):
+        return self._group
+
+    def setForceGroup(self, group):
+        self._group = int(group)
+
+    def _indices(self):
+        return np.asarray(self._molecules, dtype=np.int32).reshape(-1, 3)
+
+
+DO_1B = 0x100      # host-side selectors only: these terms have their own C-ABI entries (mbpol_eval_onebody,
+DO_DISP = 0x200    # mbpol_eval_dispersion)
 
 
 class _Engine:
@@ -212,6 +265,18 @@ class _Engine:
             _lib.check(self.L.mbpol_eval_onebody(self.h, pos.data_ptr(),
                                                  force.data_ptr() if force is not None else None, C.byref(e),
                                                  int(periodic), stream), self.h)
+        return e.value
+
+    def eval_dispersion(self, pos, force, cutoff, periodic, stream=None):
+        """TT-damped C6 dispersion; pos/force torch CUDA tensors or host numpy arrays, force accumulated into"""
+        e = C.c_double()
+        if isinstance(pos, np.ndarray):
+            _lib.check(self.L.mbpol_eval_dispersion_host(self.h, pos.ctypes.data,
+                                                         force.ctypes.data if force is not None else None, C.byref(e),
+                                                         float(cutoff), int(periodic)), self.h)
+        else:
+            _lib.check(self.L.mbpol_eval_dispersion(self.h, pos.data_ptr(), force.data_ptr() if force is not None else None,
+                                                    C.byref(e), float(cutoff), int(periodic), stream), self.h)
         return e.value
 
     def _get_list(self, fn, width):
@@ -292,6 +357,20 @@ class B200CalcMBPolOneBodyForceKernel(_B200Kernel):
         context._update_parameters(force)
 
 
+class B200CalcCustomDispersionForceKernel(_B200Kernel):
+    """stands where OpenMM's CalcCustomNonbondedForceKernel would evaluate the dispersion force of mbpol.xml:37-108"""
+    _flag = DO_DISP
+
+    @staticmethod
+    def Name():
+        return "CustomDispersionForce"
+
+    def copyParametersToContext(self, context, force):
+        if force.getNumMolecules() != self.force.getNumMolecules():
+            raise MBPolError(_lib.ECHANGED, "updateParametersInContext: The number of particles has changed")
+        context._update_parameters(force)
+
+
 class MBPolContext:
     """The part of OpenMM's System+Context the 2B/3B path needs.
 
@@ -308,9 +387,15 @@ class MBPolContext:
         self._f2 = next((f for f in self.forces if isinstance(f, MBPolTwoBodyForce)), None)
         self._f3 = next((f for f in self.forces if isinstance(f, MBPolThreeBodyForce)), None)
         self._f1 = next((f for f in self.forces if isinstance(f, MBPolOneBodyForce)), None)
-        if self._f2 is None and self._f3 is None and self._f1 is None:
+        self._fd = next((f for f in self.forces if isinstance(f, CustomDispersionForce)), None)
+        if self._f2 is None and self._f3 is None and self._f1 is None and self._fd is None:
             raise MBPolError(_lib.EINVAL, "no MBPolOneBodyForce / MBPolTwoBodyForce / MBPolThreeBodyForce given")
-        ref = self._f2 or self._f3 or self._f1
+        ref = self._f2 or self._f3 or self._f1 or self._fd
+        if self._fd is not None:
+            if not np.array_equal(self._fd._indices(), ref._indices()):
+                raise MBPolError(_lib.EINVAL, "the forces must list the same molecules")
+            if self._fd.getNonbondedMethod() == CustomDispersionForce.CutoffPeriodic and self.box is None:
+                raise MBPolError(_lib.EINVAL, "CutoffPeriodic needs a periodic box")
         if self._f1 is not None and not np.array_equal(self._f1._indices(), ref._indices()):
             raise MBPolError(_lib.EINVAL, "the forces must list the same molecules")
         if self._f1 is not None and self._f1.getNonbondedMethod() == MBPolOneBodyForce.Periodic and self.box is None:
@@ -336,7 +421,7 @@ class MBPolContext:
         self.kernels = []
         self._flags = 0
         for f, K in ((self._f1, B200CalcMBPolOneBodyForceKernel), (self._f2, B200CalcMBPolTwoBodyForceKernel),
-                     (self._f3, B200CalcMBPolThreeBodyForceKernel)):
+                     (self._f3, B200CalcMBPolThreeBodyForceKernel), (self._fd, B200CalcCustomDispersionForceKernel)):
             if f is not None:
                 k = K(K.Name(), self)
                 k.initialize(None, f)
@@ -358,8 +443,8 @@ class MBPolContext:
         self._check_same_molecules = True
 
     def _same_molecules_or_raise(self):
-        ref = self._f2 or self._f3 or self._f1
-        for other in (self._f1, self._f2, self._f3):
+        ref = self._f2 or self._f3 or self._f1 or self._fd
+        for other in (self._f1, self._f2, self._f3, self._fd):
             if other is not None and other is not ref and not np.array_equal(other._indices(), ref._indices()):
                 raise MBPolError(_lib.EINVAL, "updateParametersInContext: the forces of this context no longer list "
                                               "the same molecules")
@@ -374,7 +459,7 @@ class MBPolContext:
         host = isinstance(self._pos, np.ndarray)
         stream = None
         many = flags & (_lib.DO_2B | _lib.DO_3B)
-        overwrite = host and many and not flags & DO_1B     # the many-body call may then write f without reading it
+        overwrite = host and many and not flags & (DO_1B | DO_DISP)   # the many-body call may then write f without reading it
         if host:
             if self._force_out is not None:
                 f = self._force_out
@@ -393,6 +478,12 @@ class MBPolContext:
                                           stream)
             self.energies["CalcMBPolOneBodyForce"] = e1
             total += e1
+        if flags & DO_DISP:
+            d = self._fd
+            cutoff = 1e10 if d.getNonbondedMethod() == d.NoCutoff else d.getCutoffDistance()
+            ed = self.engine.eval_dispersion(self._pos, f, cutoff, d.getNonbondedMethod() == d.CutoffPeriodic, stream)
+            self.energies["CustomDispersionForce"] = ed
+            total += ed
         if many:
             e2, e3 = self.engine.eval_host(self._pos, f, many | (_lib.OVERWRITE_FORCES if overwrite else 0)) if host else \
                 self.engine.eval_device(self._pos, f, many, stream=stream)

@@ -208,7 +208,7 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
     std::string err;
     if (ctx->idx.reserve(sizeof(int32_t) * (3 * (size_t)ctx->n_mol + 4), err) ||
         ctx->f_mol.reserve(sizeof(double) * (9 * (size_t)ctx->n_mol + 9), err) ||
-        ctx->e_partial.reserve(sizeof(double) * 1024, err) || ctx->d_energy.reserve(sizeof(double) * 4, err))
+        ctx->e_partial.reserve(sizeof(double) * 1024, err) || ctx->d_energy.reserve(sizeof(double) * 8, err))
         return bail(MBPOL_ENOMEM, err);
     if (ctx->n_mol > 0 && cudaMemcpy(ctx->idx.ptr, cfg->particle_indices, sizeof(int32_t) * 3 * (size_t)ctx->n_mol,
                                      cudaMemcpyHostToDevice) != cudaSuccess)

@@ -48,6 +48,10 @@ struct mbpol_ctx {
     // Verlet skin (lists.cu) and on-device integrator (nve.cu)
     double skin = 0.0;
     DeviceBuf nve_force, nve_ke, nve_log, nve_msite;
+    // dispersion (dispersion.cu): its own molecule-pair list (different cutoff), force blocks and contribution index
+    TupleLists dlists;
+    ContributionIndex ci_d;
+    DeviceBuf e_d, f_d, f_mol_d;
 };
 
 // reads the stage events of the last evaluation into ctx->stats (synchronises on the last event)

@@ -48,18 +48,30 @@ __global__ void force_scatter_fixed_kernel(const double* __restrict__ f_mol, con
 
 constexpr int ESUM_BLOCK = 256, ESUM_MAX_BLOCKS = 1024;
 
-__device__ __forceinline__ double block_tree_sum(double v, double* sh) {
-    sh[threadIdx.x] = v;
+// fixed-shape block sum: warp-shuffle tree inside every warp, then the (<= 32) warp totals by the first warp; the
+// order of additions depends on nothing but the block size -> bitwise reproducible
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;                                            // lane 0 holds the total
+}
+
+__device__ __forceinline__ double block_tree_sum(double v, double* sh /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_tree_sum(v);
+    if (lane == 0) sh[warp] = v;
     __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-        __syncthreads();
+    double tot = 0.0;
+    if (warp == 0) {
+        tot = warp_tree_sum(lane < nwarp ? sh[lane] : 0.0);
+        if (lane == 0) sh[0] = tot;
     }
+    __syncthreads();
     return sh[0];
 }
 
 __global__ void energy_partial_kernel(const double* __restrict__ e, int64_t n, double* __restrict__ partial) {
-    __shared__ double sh[ESUM_BLOCK];
+    __shared__ double sh[32];
     double acc = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         acc += e[i];
@@ -68,7 +80,7 @@ __global__ void energy_partial_kernel(const double* __restrict__ e, int64_t n, d
 }
 
 __global__ void energy_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-    __shared__ double sh[ESUM_MAX_BLOCKS];
+    __shared__ double sh[32];
     const double tot = block_tree_sum(threadIdx.x < nb ? partial[threadIdx.x] : 0.0, sh);
     if (threadIdx.x == 0) *out = tot;
 }
