@@ -6,7 +6,9 @@ nonbonded method maps NoCutoff / CutoffNonPeriodic / CutoffPeriodic / PME onto t
 `addParticle([O, H1, H2])` is issued per HOH residue (mbpol.py:138-150).  Both the reduced XML shipped here
 (data/mbpol_2b3b.xml) and the reference's full python/mbpol.xml parse: only these force elements are read.
 An `<MBPolOneBodyForce>` element adds the one-body term (python/mbpol.py:12-79: NoCutoff / CutoffNonPeriodic ->
-NonPeriodic, CutoffPeriodic / PME -> Periodic, one addOneBody([O, H1, H2]) per water)."""
+NonPeriodic, CutoffPeriodic / PME -> Periodic, one addOneBody([O, H1, H2]) per water).  A `<Script>` that builds the
+TT-damped dispersion CustomNonbondedForce (python/mbpol.xml:37-108) adds a CustomDispersionForce with
+`nonbondedCutoff` as its cutoff distance and the method map of mbpol.xml:88-90 (PME -> CutoffPeriodic)."""
 from __future__ import annotations
 
 import os
@@ -14,7 +16,7 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
-from .api import MBPolContext, MBPolOneBodyForce, MBPolThreeBodyForce, MBPolTwoBodyForce
+from .api import CustomDispersionForce, MBPolContext, MBPolOneBodyForce, MBPolThreeBodyForce, MBPolTwoBodyForce
 
 DEFAULT_XML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "mbpol_2b3b.xml")
 
@@ -57,10 +59,14 @@ class ForceField:
             if el is not None:
                 self.cutoffs[tag] = float(el.attrib["cutoff_nm"])
         self.one_body = root.find("MBPolOneBodyForce") is not None
+        self.dispersion = any("tt6" in (el.text or "") and "CustomNonbondedForce" in (el.text or "")
+                              for el in root.findall("Script"))
         if not self.cutoffs and not self.one_body:
             raise ValueError("no MBPolOneBodyForce / MBPolTwoBodyForce / MBPolThreeBodyForce element in " + xml_path)
 
-    def createForces(self, pdb, nonbondedMethod=CutoffNonPeriodic):
+    def createForces(self, pdb, nonbondedMethod=CutoffNonPeriodic, nonbondedCutoff=1.0):
+        """nonbondedCutoff (nm; OpenMM's createSystem default is 1 nm) only reaches the dispersion force: the MB-pol forces
+        take their cutoffs from the XML (python/mbpol.py:99,131)"""
         if nonbondedMethod not in _METHOD:
             raise ValueError("Illegal nonbonded method for MBPolTwoBodyForce")
         forces = []
@@ -79,11 +85,20 @@ class ForceField:
             for ohh in pdb.water_indices():
                 f.addParticle(ohh)
             forces.append(f)
+        if self.dispersion:
+            d = CustomDispersionForce()
+            d.setNonbondedMethod({NoCutoff: d.NoCutoff, CutoffNonPeriodic: d.CutoffNonPeriodic, CutoffPeriodic: d.CutoffPeriodic,
+                                  PME: d.CutoffPeriodic}[nonbondedMethod])
+            d.setCutoffDistance(nonbondedCutoff)
+            for ohh in pdb.water_indices():
+                d.addMolecule(ohh)
+            forces.append(d)
         return forces
 
-    def createContext(self, pdb, nonbondedMethod=CutoffNonPeriodic, box_nm=None, **kw):
+    def createContext(self, pdb, nonbondedMethod=CutoffNonPeriodic, box_nm=None, nonbondedCutoff=1.0, **kw):
         box = box_nm if box_nm is not None else pdb.box_nm
         periodic = _METHOD[nonbondedMethod] == 1
-        ctx = MBPolContext(len(pdb.atoms), self.createForces(pdb, nonbondedMethod), box_nm=box if periodic else None, **kw)
+        ctx = MBPolContext(len(pdb.atoms), self.createForces(pdb, nonbondedMethod, nonbondedCutoff),
+                           box_nm=box if periodic else None, **kw)
         ctx.setPositions(pdb.positions)
         return ctx

@@ -76,3 +76,21 @@ def test_plain_c_client_compiles_and_links(tmp_path):
         assert r.returncode == 0 and "E_2B = 6.142078" in r.stdout
     else:
         assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+def test_two_gpu_c_client_compiles_and_runs_where_two_gpus_exist(tmp_path):
+    """examples/capi_demo_2gpu.c: NCCL collectives behind the C ABI from plain C, one thread per GPU (exit code 77 = fewer
+    than two GPUs on this machine; with two it must reproduce the single-GPU energies and forces)"""
+    import subprocess
+    from mbpol_openmm_plugin_b200 import _lib
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "capi_demo_2gpu")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "examples", "capi_demo_2gpu.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"), "-L" + libdir,
+                           "-lmbpol_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lpthread", "-lm",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode in (0, 77), r.stdout + r.stderr
+    if r.returncode == 0:
+        assert "Done" in r.stdout

@@ -34,9 +34,15 @@ def test_xml_and_pdb_parsing(tmp_path):
     assert f2.getNonbondedMethod() == f2.CutoffPeriodic and f3.getCutoff() == 0.45 and f2.getNumMolecules() == 14
     with pytest.raises(ValueError):
         field.createForces(pdb, "Ewald")
+    assert not field.dispersion                       # the reduced XML shipped here has no dispersion script
     ref_xml = "/root/reference/python/mbpol.xml"
     if os.path.exists(ref_xml):                       # the reference's full force-field file parses too
-        assert ff.ForceField(ref_xml).cutoffs == field.cutoffs
+        full = ff.ForceField(ref_xml)
+        assert full.cutoffs == field.cutoffs and full.dispersion
+        forces = full.createForces(pdb, ff.PME, nonbondedCutoff=0.9)
+        d = forces[-1]
+        assert type(d).__name__ == "CustomDispersionForce" and d.getCutoffDistance() == 0.9
+        assert d.getNonbondedMethod() == d.CutoffPeriodic and d.getNumMolecules() == 14
 
 
 @pytest.mark.gpu

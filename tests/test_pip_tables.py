@@ -49,18 +49,16 @@ def test_table_reproduces_reference_polynomial_values(name):
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 13}),
     ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 4}),
     ("pip3b", {"sym": 28, "npre": 8, "piece": 64, "dual_max": 9}),
-    ("pip3b", {"sym": 28, "npre": 8, "piece": 64, "dual_max": 9, "run_max": 4, "fall": 0}),
-    ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 4, "run_max": 3, "fall": 0, "nacc": 3}),
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 32, "group": 2}),
     ("pip2b", {"sym": 16, "skeleton_weight": 0}), ("pip3b", {"sym": 24, "skeleton_weight": 0, "fall": 0})])
 def test_command_stream_matches_table(name, opts, tmp_path):
     """python interpreter of the packed stream (the same records the GPU kernel executes) vs the monomial definition"""
-    meta, words, masks, phases, dual, runs = gen_interp.generate(name, str(tmp_path), **opts)
+    meta, words, masks, phases, dual = gen_interp.generate(name, str(tmp_path), **opts)
     t = dict(np.load(os.path.join(DATA, name + ".npz")))
     rng = np.random.default_rng(11)
     for _ in range(2):
         x = rng.uniform(0.05, 1.6, int(t["n_vars"]))
-        E, G = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, phases, dual, runs)
+        E, G = gen_interp.interpret(name, words, x, meta["chunk_bytes"], masks, phases, dual)
         Er, Gr = extract_pip.eval_table(t, x)
         assert abs(E - Er) <= 1e-13 * max(1.0, abs(Er))
         assert np.abs(G - Gr).max() <= 1e-13 * np.abs(Gr).max()

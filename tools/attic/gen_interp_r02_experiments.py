@@ -1,43 +1,11 @@
-"""Code generator: monomial table -> cache-resident adjoint-Horner evaluator (command stream + small sm_100a PTX kernel).
-
-The polynomial E(x) = sum_m a[c_m] prod_{v in m} x_v (data/pip{2b,3b}.npz, degree <= 4) is factored as a greedy
-multivariate Horner tree and value + reverse-mode gradient are computed in ONE depth-first pass:
-
-    node(M, adj):  v = const(M)
-       leaf  a_k x_i :  v = fma(a_k, x_i, v)      g_i = fma(a_k, adj, g_i)
-       inner x_i (..):  w = node(M / x_i, adj x_i)  v = fma(x_i, w, v)   g_i = fma(adj, w, g_i)
-
-Fully unrolled this is 1.4 MB of SASS and instruction-fetch bound (profiles/r01_*; tools/attic/gen_horner_r01.py), so
-the program is DATA: the tree is serialised depth-first into a command stream and a few-thousand-instruction kernel
-interprets it, one thread per tuple, all per-tuple state in registers:
-
-    ENTER_d k, c0  : push (v, a);  a *= x_k;  v = c0               (x_k: dynamic index -> shared-memory copy of x)
-    LEAVE_d k      : w = v; pop (v, a);  v += x_k w;  g_k += a w   (g_k: dynamic -> shared-memory accumulator)
-    SIBLING_d      : LEAVE_d k_old + ENTER_d k_new, c0 in one record
-    MASK_h coefs   : for every register slot j of handler h:  v += c_j x_j ;  g_j += c_j a
-    LEAFNODE_h     : ENTER + MASK_h + LEAVE fused (nodes without inner children: 83 % of all nodes)
-    DUAL_h         : two consecutive LEAFNODE_h records (siblings) in one dispatch, coefficients interleaved
-    TRANSITION_p   : end of symmetry phase p (see below)
-    NEXT / END     : flip the stream buffers / finish
-
-Symmetry phases.  Every variable is a function of ONE site-site distance; a hydrogen (or lone-pair)
-swap inside one molecule permutes the variables and leaves the polynomial invariant.  A node whose leaf coefficients
-are invariant under a set S of swaps is a linear form in the S-ORBIT SUMS of the variables, and its gradient
-contribution is the same number for every member of an orbit.  The stream is run in PHASES, one per subgroup S that
-pays for itself: the registers hold the orbit sums of that phase (slot = lowest variable of the orbit), the leaf
-handlers work on slots, TRANSITION scatters the register gradients to the orbit members and loads the next phase.
-Leaf handlers are specialised on register-slot SETS chosen by an agglomerative merge (`merge_library`); payloads are
-dense per handler (zero padding), so a handler needs no indexing at all.
-
-DUAL records (round 2).  90 % (3B) / 95 % (2B) of the leaf-node records sit next to a sibling with the same handler.
-One handler evaluates both: four independent value chains instead of two (the dependent-issue stalls of the value FMAs
-were the largest stall reason of the round-1 kernel), the second value FMA of a slot reads x_j from the operand-reuse
-cache (a DFMA with three fresh 64-bit register operands issues every third cycle, not every second,
-profiles/r01_dfma_operand_microbench.md), and header / dispatch / address arithmetic are paid once per two records.
-
-The round-1 experiments that lost (variable-class kernels, STATIC handlers, constant-bank stream, x_k prefetch, ...)
-live in tools/attic/gen_interp_r01.py together with their measurements' pointers; this file is the shipped path plus
-the knobs that are still being measured.
+"""ROUND-2 EXPERIMENTS, not the shipped generator (that is tools/gen_interp.py): this copy additionally has
+  * RUN chains (`--run N`): up to N equal leaf units per dispatch, the bodies laid out back to back (static fall-through);
+  * `--nacc 3|4` value chains per leaf node; uniform "anchors" (PIP_NO_ANCHOR / PIP_MASK_FALL environment knobs).
+Measured on B200 (profiles/r02_microbench_pip_variants.log): RUN chains execute 5 % fewer instructions and 45 % fewer
+branches but run 8 % SLOWER, because without the `setp + @p brx.idx` pattern of the duplicated ("fall") handlers in at least
+~58 % of the dispatch sites ptxas keeps the opcode web in vector registers and emits BRX R instead of BRXU (ncu:
+branch_resolving 0.34 instead of 0.06 stall cycles per issue); no PTX idiom tried here (brx.idx.uni, redux.sync, never-taken
+uniform branches) flips that decision without costing more than it gains.  3 / 4 value chains: -4 % / wrong (register clash).
 """
 from __future__ import annotations
 
@@ -182,9 +150,10 @@ def merge_library(req, K):
     return sets
 
 
-def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
-    """-> (records, masks, phases, dual).  records: (opcode, k, payload doubles); masks: handler slot tuples; phases: list
-    of orbit lists (phase 0 = identity); dual: handler ids that have a DUAL record type, in opcode order."""
+def serialise(name, tab, K, skeleton_weight=40, dual_max=0, run_max=1):
+    """-> (records, masks, phases, dual, runs).  records: (opcode, k, payload doubles); masks: handler slot tuples; phases:
+    list of orbit lists (phase 0 = identity); dual: handler ids that have a DUAL record type, in opcode order; runs: list of
+    (length, unit opcode) of the RUN opcodes, in opcode order (see below)."""
     nv = int(tab["n_vars"])
     coef = tab["coef"]
     monos = [(tuple(int(v) for v in row if v != PAD), int(c)) for row, c in zip(tab["mono_vars"], tab["mono_coef"])]
@@ -327,14 +296,47 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
                 out.append(recs[i])
                 i += 1
         recs = out
-    return recs, masks, phases, dual
+    # RUN_{L,u}: L consecutive records of the same leaf unit u (LEAFNODE_h or DUAL_i), 2 <= L <= run_max.  The kernel lays
+    # out run_max bodies of the unit back to back, only the last one ends with a dispatch; a run enters the chain L bodies
+    # before its end and FALLS THROUGH from record to record: one indirect branch (the most expensive instruction of the
+    # interpreter: ~40 cycles of fetch redirect + a serial table look-up in the uniform datapath) per run instead of per
+    # record.  Only the FIRST record of a run carries the RUN opcode; the others keep their unit opcode, which nobody reads.
+    runs = []
+    if run_max > 1:
+        dbase = base + MAX_DEPTH
+        rbase = dbase + len(dual)
+        unit = lambda op: OP_MASK + nm <= op < OP_MASK + 2 * nm or op >= dbase  # noqa: E731
+        out, i = [], 0
+        while i < len(recs):
+            op = recs[i][0]
+            j = i
+            while unit(op) and j < len(recs) and recs[j][0] == op:
+                j += 1
+            if j - i < 2:
+                out.append(recs[i])
+                i += 1
+                continue
+            while i < j:                                 # split long runs into chunks of at most run_max
+                L = min(run_max, j - i)
+                if L >= 2:
+                    if (L, op) not in runs:
+                        runs.append((L, op))
+                    out.append((("RUN", L, op), recs[i][1], recs[i][2]))
+                    out.extend(recs[i + 1:i + L])
+                else:
+                    out.append(recs[i])
+                i += L
+        runs.sort(key=lambda r: (r[1], -r[0]))
+        rid = {r: rbase + q for q, r in enumerate(runs)}
+        recs = [((rid[(op[1], op[2])], k, pl) if isinstance(op, tuple) else (op, k, pl)) for op, k, pl in out]
+    return recs, masks, phases, dual, runs
 
 
 def rec_words(n_payload):
     return 1 + (n_payload if n_payload % 2 else n_payload + 1)
 
 
-def pack(recs, chunk_bytes):
+def pack(recs, chunk_bytes, run_len=None):
     """u64 words, organised in chunks of ``chunk_bytes`` that the kernel stages through shared memory one at a time.
     Inside a chunk, word 0 is padding so that every record header sits at byte offset 8 (mod 16) and every payload is
     16-byte aligned (payloads are padded to an odd number of words).  No record straddles a chunk: the last record of a
@@ -345,8 +347,11 @@ def pack(recs, chunk_bytes):
     chunks = []
     cur = [0]
     hdrs = []                                     # (chunk index, word index, op) of every header in execution order
-    for op, k, payload in recs:
+    run_len = run_len or {}
+    for ri, (op, k, payload) in enumerate(recs):
         need = rec_words(len(payload))
+        if op in run_len:                         # a run falls through from record to record: it must not straddle a chunk
+            need = sum(rec_words(len(r[2])) for r in recs[ri:ri + run_len[op]])
         if len(cur) + need + 18 > cw:             # room for OP_NEXT + the look-ahead words the handlers preload
             hdrs.append((len(chunks), len(cur), OP_NEXT))
             cur += [OP_NEXT, 0]
@@ -368,7 +373,7 @@ def pack(recs, chunk_bytes):
     return np.array([w for c in chunks for w in c], dtype=np.uint64)
 
 
-def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
+def interpret(name, words, x, chunk_bytes, masks, phases, dual=(), runs=()):
     """numpy/python reference interpreter of the packed stream (used by the CPU tests): the same records, in the same
     order, with the same meaning as the PTX handlers below."""
     cw = chunk_bytes // 8
@@ -381,14 +386,21 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
     t_base = OP_MASK + 2 * nm
     s_base = t_base + len(phases)
     d_base = s_base + MAX_DEPTH
+    r_base = d_base + len(dual)
     pc = 1
     v, a = 0.0, 1.0
     stack = []
     nxt = int(words[0]) & 0xFFFFFFFF
+    pending = 0                                # records of the current run still to execute with the run's unit opcode
     while True:
         hdr = int(words[pc])
         op, k = hdr & 0xFFFFFFFF, hdr >> 32
         op, nxt = nxt, op
+        if pending:                            # inside a run the kernel falls through: the opcode is not consulted
+            op, pending = run_unit, pending - 1
+        elif op >= r_base:
+            pending, run_unit = runs[op - r_base][0] - 1, runs[op - r_base][1]
+            op = run_unit
         if op == OP_END:
             return v, g
         if op == OP_NEXT:
@@ -458,7 +470,7 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
 
 
 def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_blocks=1, piece=64, fall=(), npre=8,
-               fall_copies=2, group=4, maxnreg=0):
+               fall_copies=2, group=4, maxnreg=0, runs=(), nacc=2):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 mode)
@@ -481,7 +493,8 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     t_base = OP_MASK + 2 * nm
     s_base = t_base + len(phases)
     d_base = s_base + MAX_DEPTH
-    n_ops = d_base + len(dual)
+    r_base = d_base + len(dual)
+    n_ops = r_base + len(runs)
     SG = nv * NT * 8                   # smem: x copy | g accumulators | 2 stream buffers
     SB = 2 * nv * NT * 8
     out = []
@@ -548,10 +561,23 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         w(f"ld.shared.v2.u32 {{%nop, %nk}}, [%sp+{8 * nwords}];")
 
     fall_state = [None]
+    uniform_anchors = not os.environ.get('PIP_NO_ANCHOR')
 
-    def tail(nwords, preloaded=0):
+    def tail(nwords, preloaded=0, dispatch=True, anchor=False):
         preload(8 * nwords, preloaded)
         w(f"add.u32 %sp, %sp, {8 * nwords};")
+        if not dispatch:                    # a body inside a RUN chain: the next record is handled by the code that follows
+            return
+        if anchor and uniform_anchors:
+            # Uniform anchor.  %op / %nop form ONE live-range web across all handlers (they meet at every indirect
+            # branch).  ptxas keeps that web in UNIFORM registers -- and then emits every dispatch as BRXU with the
+            # jump-table look-up hoisted to the top of the handler -- only if enough of the web's uses want a uniform
+            # operand (measured on the PTX of this file: 20 predicated dispatches flip all 97, 10 flip none); with vector
+            # registers it emits BRX R and `branch_resolving` becomes a top stall reason (ncu: 0.34 instead of 0.06 stall
+            # cycles per issue, 8 % of the kernel time).  The rarely executed handlers (ENTER / LEAVE / MASK / TRANSITION:
+            # 9 % of the records) therefore dispatch through a never-failing uniform predicate; it costs them a BRA.U.
+            w("setp.ne.u32 %pself, %op, 0x7fffffff; @%pself brx.idx %op, TBL; bra.uni FINISH;")
+            return
         if fall_state[0] is not None:
             # a second copy of this handler follows: when the next record has the same opcode no branch is taken
             w(f"setp.ne.u32 %pself, %op, {fall_state[0]}; @%pself brx.idx %op, TBL;")
@@ -589,7 +615,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         w("mov.f64 %vc, %n0; mov.f64 %vd, 0d0000000000000000;")
         preload(16)
         w(f"mul.rn.f64 %ac, %ac, %xk{d};")
-        tail(2, NPRE)
+        tail(2, NPRE, anchor=True)
     # ---- LEAVE_d
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_LEAVE + d - 1}:")
@@ -600,10 +626,10 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         w(f"mov.f64 %ac, %as{d};")
         w(f"fma.rn.f64 %vc, %xk{d}, %w, %vs{d}; mov.f64 %vd, %vt{d};")
         w("fma.rn.f64 %gk, %ac, %w, %gk; st.shared.f64 [%addr], %gk;")
-        tail(2, NPRE)
+        tail(2, NPRE, anchor=True)
 
     # ---- MASK_h and fused LEAFNODE_h
-    def block_handler(label, m, fused):
+    def block_handler(label, m, fused, dispatch=True):
         """loads first, then `group` value FMAs on two chains alternating with the `group` gradient FMAs of the same
         slots; once both FMAs of a 16-byte payload piece are issued its registers are dead and the same piece of the NEXT
         record is loaded into them; the chain reduction + parent update close the record."""
@@ -621,7 +647,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
             else:
                 w(f"ld.shared.f64 {coef(i)}, [%sp+{8 + 8 * i}];")
         assert n - NPRE <= 64
-        acc, adj = (["%u0", "%u1"], "%a0") if fused else (["%vc", "%vd"], "%ac")
+        acc, adj = ([f"%u{q}" for q in range(nacc)], "%a0") if fused else (["%vc", "%vd"], "%ac")
         started = set() if fused else {"%vc", "%vd"}
         vops, gops = [], []
         const0 = None                                        # the node constant starts chain %u0 as the addend of its
@@ -631,7 +657,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                 const0 = c
                 vops.append(None)
                 continue
-            a = acc[i % 2]
+            a = acc[i % len(acc)]
             if a in started:
                 vops.append(f"fma.rn.f64 {a}, {c}, %x{j}, {a};")
             elif a == "%u0" and const0 is not None:
@@ -664,14 +690,21 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                     done = p2 + 2
         preload(8 * nwords, done)
         if fused:
-            if "%u1" in started:
-                w("add.rn.f64 %u0, %u0, %u1;")
+            live = [a for a in acc if a in started]
+            while len(live) > 1:                             # pairwise reduction of the value chains
+                nxt = []
+                for q in range(0, len(live) - 1, 2):
+                    w(f"add.rn.f64 {live[q]}, {live[q]}, {live[q + 1]};")
+                    nxt.append(live[q])
+                if len(live) % 2:
+                    nxt.append(live[-1])
+                live = nxt
             w("fma.rn.f64 %vc, %xk0, %u0, %vc;")
             w("fma.rn.f64 %gk, %ac, %u0, %gk;")
             w("st.shared.f64 [%addr], %gk;")
-        tail(nwords, NPRE)
+        tail(nwords, NPRE, dispatch, anchor=not fused)
 
-    def dual_handler(label, m):
+    def dual_handler(label, m, dispatch=True):
         """two sibling LEAFNODE records A, B of the same handler.  Payload words: c0_A, c0_B, then (c_Aj, c_Bj) per slot.
         A accumulates on %u0 / %u1 and updates the parent through %vc, B on %u2 / %u3 through %vd; the two value FMAs of
         a slot are adjacent and share x_j (operand reuse), the gradient FMAs of a group run A-then-B so that each
@@ -730,12 +763,29 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         w("fma.rn.f64 %gkb, %ac, %u2, %gkb;")
         w("st.shared.f64 [%addr], %gk;")
         w("st.shared.f64 [%addrb], %gkb;")
-        tail(nwords, NPRE)
+        tail(nwords, NPRE, dispatch)
 
     for mi, m in enumerate(masks):
-        block_handler(f"H{OP_MASK + mi}", m, False)
+        if os.environ.get("PIP_MASK_FALL"):
+            fall_state[0] = OP_MASK + mi
+            block_handler(f"H{OP_MASK + mi}", m, False)
+            fall_state[0] = None
+            block_handler(f"H{OP_MASK + mi}B", m, False)
+        else:
+            block_handler(f"H{OP_MASK + mi}", m, False)
+    run_ids = {r: r_base + q for q, r in enumerate(runs)}
+
+    def chain(unit_op, emit):
+        """RUN chain of one leaf unit: bodies without dispatch for the longest run down to 2, then the unit's own handler"""
+        longest = max([L for L, u in runs if u == unit_op], default=1)
+        for L in range(longest, 1, -1):
+            lab = f"H{run_ids[(L, unit_op)]}" if (L, unit_op) in run_ids else f"R{unit_op}_{L}"
+            emit(lab, False)
+        return longest
+
     for mi, m in enumerate(masks):
         op = OP_MASK + nm + mi
+        chain(op, lambda lab, disp, m=m: block_handler(lab, m, True, disp))
         copies = fall_copies if op in fall else 1
         # back-to-back copies: every copy but the last falls through into the next one when the next record has the
         # same opcode (runs of equal records are the rule: symmetry-related siblings)
@@ -755,7 +805,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                 w(f"ld.shared.f64 %x{o[0]}, [%sx+{o[0] * NT * 8}]; mov.f64 %g{o[0]}, 0d0000000000000000;")
                 for i in o[1:]:
                     w(f"ld.shared.f64 %w, [%sx+{i * NT * 8}]; add.rn.f64 %x{o[0]}, %x{o[0]}, %w;")
-        tail(2)
+        tail(2, anchor=True)
     # ---- SIBLING_d: LEAVE_d k_old + ENTER_d k_new, c0 in one record (k = k_new | k_old << 8)
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{s_base + d - 1}:")
@@ -772,6 +822,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         tail(2, NPRE)
     # ---- DUAL_i
     for di, h in enumerate(dual):
+        chain(d_base + di, lambda lab, disp, h=h: dual_handler(lab, masks[h], disp))
         dual_handler(f"H{d_base + di}", masks[h])
     # ---- epilogue: the last TRANSITION has scattered every register gradient
     w("FINISH:")
@@ -791,14 +842,18 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     return out, SB + 2 * CH
 
 
-def count_fp64(recs, masks, phases, dual):
+def count_fp64(recs, masks, phases, dual, runs=()):
     nm = len(masks)
     t_base = OP_MASK + 2 * nm
     s_base = t_base + len(phases)
     d_base = s_base + MAX_DEPTH
+    r_base = d_base + len(dual)
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
+        if op >= r_base:                         # first record of a run: counted like its unit (the others follow as units)
+            hist["runs"] += 1
+            op = runs[op - r_base][1]
         if op >= d_base:
             n_fp += 2 * (2 * len(masks[dual[op - d_base]]) + 4)
             hist["dual"] += 1
@@ -829,19 +884,20 @@ def count_fp64(recs, masks, phases, dual):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_weight=40, fall=4, npre=8, fall_copies=2,
-             dual_max=0, group=4, maxnreg=0):
-    """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual)."""
+             dual_max=0, group=4, maxnreg=0, run_max=1, nacc=2):
+    """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual, runs)."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
     assert nv == NV[name]
     chunk = block * piece
-    recs, masks, phases, dual = serialise(name, tab, sym, skeleton_weight, dual_max)
+    recs, masks, phases, dual, runs = serialise(name, tab, sym, skeleton_weight, dual_max, run_max)
     nm = len(masks)
-    runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
+    same = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
     lo, hi = OP_MASK + nm, OP_MASK + 2 * nm
-    fall_ops = tuple(sorted(op for op, c in runs.items() if fall and c >= fall and lo <= op < hi))
-    words = pack(recs, chunk)
-    n_fp, hist = count_fp64(recs, masks, phases, dual)
+    fall_ops = tuple(sorted(op for op, c in same.items() if fall and c >= fall and lo <= op < hi))
+    r_base = OP_MASK + 2 * nm + len(phases) + MAX_DEPTH + len(dual)
+    words = pack(recs, chunk, {r_base + q: L for q, (L, _) in enumerate(runs)})
+    n_fp, hist = count_fp64(recs, masks, phases, dual, runs)
     symbol = f"{name}_stream0"
     lines = ["// GENERATED by tools/gen_interp.py -- command-stream adjoint-Horner PIP evaluator (see the tool's docstring).",
              ".version 8.7", ".target sm_100a", ".address_size 64", "", ".extern .shared .align 16 .b8 pip_smem[];", "",
@@ -851,7 +907,7 @@ def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_
     lines.append("};")
     entry = f"{name}_eval"
     kl, smem = kernel_ptx(name, entry, symbol, masks, nv, phases, dual, block, min_blocks, piece, fall_ops, npre,
-                          fall_copies, group, maxnreg)
+                          fall_copies, group, maxnreg, runs, nacc)
     lines += [""] + kl
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
@@ -859,10 +915,10 @@ def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_
     meta = {"name": name, "block": block, "smem_bytes": smem, "fp64_instr": n_fp, "chunk_bytes": chunk,
             "records": dict(hist), "kind": "interp-sym",
             "kernels": [{"entry": entry, "vars": nv, "masks": nm, "stream_bytes": int(words.nbytes), "fp64_instr": n_fp}],
-            "phases": phases, "handlers": [len(m) for m in masks], "dual": list(dual)}
+            "phases": phases, "handlers": [len(m) for m in masks], "dual": list(dual), "runs": [list(r) for r in runs]}
     with open(os.path.join(out_dir, f"{name}_meta.json"), "w") as fh:
         json.dump(meta, fh)
-    return meta, words, masks, phases, dual
+    return meta, words, masks, phases, dual, runs
 
 
 def main():
@@ -877,6 +933,8 @@ def main():
         ap.add_argument(f"--npre{two}", type=int, default=d[3], help="payload words of the next record every handler pre-loads")
         ap.add_argument(f"--dual{two}", type=int, default=d[4], help="DUAL records for handlers of at most N slots")
         ap.add_argument(f"--maxnreg{two}", type=int, default=0, help="register cap (0: none); see kernel_ptx")
+        ap.add_argument(f"--run{two}", type=int, default=1, help="RUN chains: up to N equal leaf units per dispatch (1: off)")
+        ap.add_argument(f"--nacc{two}", type=int, default=2, help="value chains per leaf node")
     ap.add_argument("--skeleton-weight", type=int, default=40)
     ap.add_argument("--fall", type=int, default=4, help="duplicate leaf handlers that follow themselves at least N times")
     ap.add_argument("--fall-copies", type=int, default=2)
@@ -889,7 +947,8 @@ def main():
         t = "2" if name == "pip2b" else ""
         meta, *_ = generate(name, args.out, getattr(args, "block" + t), args.min_blocks, getattr(args, "piece" + t),
                             getattr(args, "sym" + t), args.skeleton_weight, args.fall, getattr(args, "npre" + t),
-                            args.fall_copies, getattr(args, "dual" + t), args.group, getattr(args, "maxnreg" + t))
+                            args.fall_copies, getattr(args, "dual" + t), args.group, getattr(args, "maxnreg" + t),
+                            getattr(args, "run" + t), getattr(args, "nacc" + t))
         print({k: v for k, v in meta.items() if k != "phases"})
 
 
