@@ -47,7 +47,7 @@ def test_table_reproduces_reference_polynomial_values(name):
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64}),
     ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 16}),
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 13}),
-    ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 4}),
+    ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 4, "slim": True, "anchors": True}),
     ("pip3b", {"sym": 28, "npre": 8, "piece": 64, "dual_max": 9}),
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 32, "group": 2}),
     ("pip2b", {"sym": 16, "skeleton_weight": 0}), ("pip3b", {"sym": 24, "skeleton_weight": 0, "fall": 0})])
@@ -81,7 +81,7 @@ def test_shipped_generator_settings_are_tested():
     from mbpol_openmm_plugin_b200 import build
     a = build.GEN_ARGS
     assert (a["sym2"], a["sym"], a["npre"], a["piece"], a["block"], a["dual"]) == (12, 28, 8, 64, 256, 9)
-    assert (a["block2"], a["piece2"], a["npre2"], a["dual2"]) == (384, 32, 4, 4)
+    assert (a["block2"], a["piece2"], a["npre2"], a["dual2"], a["slim2"], a["anchors2"]) == (384, 32, 4, 4, 1, 1)
 
 
 @pytest.mark.parametrize("name", ["pip2b", "pip3b"])
@@ -122,3 +122,21 @@ def test_generator_and_cuda_kernels_agree_on_the_variable_table(name, macro, sit
     pairs, _ = gen_interp._sites(name)
     assert sorted(table) == list(range(len(pairs)))
     assert [table[i] for i in range(len(pairs))] == [frozenset(p) for p in pairs]
+
+
+@pytest.mark.parametrize("name", ["pip2b", "pip3b"])
+def test_shipped_cubins_dispatch_through_the_uniform_datapath(name):
+    """ptxas keeps the opcode of the command stream either in uniform registers (dispatch = BRXU, jump-table read hoisted)
+    or in vector registers (BRX R: 8 % slower, `branch_resolving` stalls) -- a global decision that flips with small changes
+    of the generated PTX (tools/gen_interp.py, tail()).  The shipped kernels must be in the first regime, with no spills."""
+    import shutil
+    import subprocess
+    gen = os.path.join(ROOT, "mbpol_openmm_plugin_b200", "csrc", "gen")
+    cubin = os.path.join(gen, name + ".cubin")
+    if not os.path.exists(cubin) or shutil.which("cuobjdump") is None:
+        pytest.skip("library not built here")
+    sass = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True, check=True).stdout
+    assert sass.count("BRXU") >= 40 and sass.count("BRX R") <= 2
+    assert "DFMA" in sass and "LDGSTS" in sass                   # FP64 FMAs, cp.async stream staging
+    log = open(os.path.join(gen, name + ".ptxas.log")).read()
+    assert "0 bytes spill stores" in log

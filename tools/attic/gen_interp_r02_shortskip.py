@@ -56,10 +56,19 @@ DATA = os.path.join(HERE, "..", "mbpol_openmm_plugin_b200", "data")
 GEN = os.path.join(HERE, "..", "mbpol_openmm_plugin_b200", "csrc", "gen")
 
 NV = {"pip2b": 31, "pip3b": 36}
-OP_END, OP_ENTER, OP_LEAVE, OP_NEXT, OP_MASK = 0, 1, 4, 7, 8
-# ENTER_d = 1..3, LEAVE_d = 4..6, MASK_h = 8 + h, LEAFNODE_h = 8 + nm + h, TRANSITION_p = 8 + 2 nm + p,
-# SIBLING_d = 8 + 2 nm + n_phases + d - 1, DUAL_i = 8 + 2 nm + n_phases + 3 + i (i indexes the handlers that have one)
+OP_END, OP_ENTER, OP_LEAVE, OP_NEXT, OP_TRANS = 0, 1, 4, 7, 8
+# ENTER_d = 1..3, LEAVE_d = 4..6, TRANSITION_p = 8 + p, SIBLING_d = 8 + n_phases + d - 1  -- all records with at most two
+# payload words come first: "opcode < n_short" is the test the look-ahead loads are predicated on --
+# then MASK_h, LEAFNODE_h (h < nm) and DUAL_i (i indexes the handlers that have one)
 MAX_DEPTH = 3
+
+
+def op_bases(nm, n_phases):
+    """-> (t_base, s_base, m_base, l_base, d_base): first opcode of TRANSITION, SIBLING, MASK, LEAFNODE, DUAL"""
+    t = OP_TRANS
+    s = t + n_phases
+    m = s + MAX_DEPTH
+    return t, s, m, m + nm, m + 2 * nm
 
 
 def split_greedy(monos):
@@ -264,6 +273,7 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
         return s
     leaf_phases(root)
     recs = []
+    t_base, s_base, m_base, l_base, d_base = op_bases(nm, len(phases))
 
     def payload(node):
         need = cls[id(node)][1]
@@ -282,14 +292,14 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
         kids.sort(key=order)
         if depth > 0 and not kids:
             assert own
-            recs.append((OP_MASK + nm + h, node.var, [const] + payload(node)))
+            recs.append((l_base + h, node.var, [const] + payload(node)))
             return
         if depth > 0:
             recs.append((OP_ENTER + depth - 1, node.var, [const]))
         else:
             assert node.const is None
         if own:
-            recs.append((OP_MASK + h, 0, payload(node)))
+            recs.append((m_base + h, 0, payload(node)))
         for k in kids:
             emit(k, depth + 1, p)
         if depth > 0:
@@ -297,10 +307,10 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
     for p in range(len(phases)):
         if p in leafph[id(root)]:
             emit(root, 0, p)
-        recs.append((OP_MASK + 2 * nm + p, 0, []))
+        recs.append((t_base + p, 0, []))
     recs.append((OP_END, 0, []))
     # SIBLING_d = LEAVE_d k_old immediately followed by ENTER_d k_new, c0: one record (k = k_new | k_old << 8)
-    base, out, i = OP_MASK + 2 * nm + len(phases), [], 0
+    base, out, i = s_base, [], 0
     while i < len(recs):
         op, k, pl = recs[i]
         if OP_LEAVE <= op < OP_NEXT and i + 1 < len(recs) and recs[i + 1][0] == op - OP_LEAVE + OP_ENTER:
@@ -314,10 +324,10 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
     # dual_max slots: k = k_A | k_B << 8, payload = c0_A, c0_B, c_A1, c_B1, c_A2, c_B2, ... (interleaved)
     dual = [h for h in range(nm) if len(masks[h]) <= dual_max]
     if dual:
-        dbase, out, i = base + MAX_DEPTH, [], 0
+        dbase, out, i = d_base, [], 0
         while i < len(recs):
             op, k, pl = recs[i]
-            h = op - OP_MASK - nm
+            h = op - l_base
             if 0 <= h < nm and h in dual and i + 1 < len(recs) and recs[i + 1][0] == op:
                 kb, plb = recs[i + 1][1], recs[i + 1][2]
                 assert kb != k and len(pl) == len(plb)
@@ -378,9 +388,7 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
     xr, gr = x.copy(), np.zeros(nv)        # register slots: orbit sums / orbit gradients of the current phase
     f = words.view(np.float64)
     nm = len(masks)
-    t_base = OP_MASK + 2 * nm
-    s_base = t_base + len(phases)
-    d_base = s_base + MAX_DEPTH
+    t_base, s_base, m_base, l_base, d_base = op_bases(nm, len(phases))
     pc = 1
     v, a = 0.0, 1.0
     stack = []
@@ -404,24 +412,6 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
             v += xk * w
             g[k] += a * w
             pc += 2
-        elif op < OP_MASK + nm:
-            m = masks[op - OP_MASK]
-            for q, j in enumerate(m):
-                c = f[pc + 1 + q]
-                v += c * xr[j]
-                gr[j] += c * a
-            pc += rec_words(len(m))
-        elif op < t_base:                                   # LEAFNODE_h: ENTER k, const; MASK_h; LEAVE k
-            m = masks[op - OP_MASK - nm]
-            a2 = a * x[k]
-            u = f[pc + 1]
-            for q, j in enumerate(m):
-                c = f[pc + 2 + q]
-                u += c * xr[j]
-                gr[j] += c * a2
-            v += x[k] * u
-            g[k] += a * u
-            pc += rec_words(1 + len(m))
         elif op < s_base:                                   # TRANSITION_p
             p = op - t_base
             for o in phases[p]:
@@ -434,7 +424,7 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
                         xr[o[0]] += x[i]
                     gr[o[0]] = 0.0
             pc += 2
-        elif op < d_base:                                   # SIBLING_d: LEAVE k_old + ENTER k_new, c0
+        elif op < m_base:                                   # SIBLING_d: LEAVE k_old + ENTER k_new, c0
             w = v
             v, a, xk = stack.pop()
             v += xk * w
@@ -443,6 +433,24 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
             a = a * x[k & 0xFF]
             v = f[pc + 1]
             pc += 2
+        elif op < l_base:
+            m = masks[op - m_base]
+            for q, j in enumerate(m):
+                c = f[pc + 1 + q]
+                v += c * xr[j]
+                gr[j] += c * a
+            pc += rec_words(len(m))
+        elif op < d_base:                                   # LEAFNODE_h: ENTER k, const; MASK_h; LEAVE k
+            m = masks[op - l_base]
+            a2 = a * x[k]
+            u = f[pc + 1]
+            for q, j in enumerate(m):
+                c = f[pc + 2 + q]
+                u += c * xr[j]
+                gr[j] += c * a2
+            v += x[k] * u
+            g[k] += a * u
+            pc += rec_words(1 + len(m))
         else:                                               # DUAL_i: two sibling leaf nodes, interleaved payload
             m = masks[dual[op - d_base]]
             for s, kk in enumerate((k & 0xFF, k >> 8)):
@@ -458,7 +466,7 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
 
 
 def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_blocks=1, piece=64, fall=(), npre=8,
-               fall_copies=2, group=4, maxnreg=0, slim=False, anchors=False):
+               fall_copies=2, group=4, maxnreg=0, slim=False):
     """One interpreter kernel
 
         {entry}(const double* x /*[nv][ld]*/, double* out /*[1+nv][ld]: E, dE/dx*/, u32 n, u32 ld, u32 mode)
@@ -478,9 +486,8 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     CH = NT * piece                    # chunk bytes = one piece per thread
     assert piece > 16 and piece % 16 == 0 and npre % 2 == 0
     nm = len(masks)
-    t_base = OP_MASK + 2 * nm
-    s_base = t_base + len(phases)
-    d_base = s_base + MAX_DEPTH
+    t_base, s_base, m_base, l_base, d_base = op_bases(nm, len(phases))
+    n_short = m_base                   # every opcode below has at most two payload words
     n_ops = d_base + len(dual)
     SG = nv * NT * 8                   # smem: x copy | g accumulators | 2 stream buffers
     SB = 2 * nv * NT * 8
@@ -497,7 +504,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     w(".reg .f64 " + ", ".join(f"%vs{d}, %vt{d}, %as{d}, %xk{d}" for d in range(1, MAX_DEPTH + 1)) + ";")
     w(".reg .u64 %px, %po, %off, %ldb, %gs; .reg .u32 %n, %ld, %t, %tc, %r<4>, %op, %k, %nop, %nk, %sx, %sg, %addr;")
     w(".reg .u32 %sp, %bufcur, %bufoth, %mine, %ka, %kb, %addrb; .reg .f64 %xkb, %gkb;")
-    w(".reg .pred %valid, %pacc, %pself, %pscale; .reg .u32 %acc, %accb;")
+    w(".reg .pred %valid, %pacc, %pself, %pscale, %plong; .reg .u32 %acc, %accb;")
     w("ld.param.u32 %acc, [p_acc]; and.b32 %accb, %acc, 1; setp.ne.u32 %pacc, %accb, 0;")
     w("and.b32 %accb, %acc, 2; setp.ne.u32 %pscale, %accb, 0;")
     w("ld.param.u64 %px, [p_x]; ld.param.u64 %po, [p_out]; ld.param.u32 %n, [p_n]; ld.param.u32 %ld, [p_ld];")
@@ -538,29 +545,30 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     w("TBL: .branchtargets " + ", ".join(f"H{i}" for i in range(n_ops)) + ";")
 
     def preload(byte_off, start=0):
-        """payload words start..NPRE of the record at %sp+byte_off -> %n regs (garbage past short records: unused)"""
+        """payload words start..NPRE of the record at %sp+byte_off -> %n regs.  Words past the first pair are only fetched
+        when that record is long (%plong: its opcode, which the handler knows on entry, is not one of the first n_short
+        opcodes, the record types with at most two payload words): 9 % of the uniform shared-memory wavefronts
+        of the 3B stream were look-ahead loads past the end of 1-word records (SIBLING / ENTER / LEAVE), and the
+        shared-memory pipe is the unit this kernel saturates (ncu: L1/TEX throughput 88 %)."""
         for q in range(start, NPRE, 2):
-            w(f"ld.shared.v2.f64 {{%n{q}, %n{q + 1}}}, [%sp+{byte_off + 8 + 8 * q}];")
+            pred = "@%plong " if (q >= 2 and short_skip) else ""
+            w(f"{pred}ld.shared.v2.f64 {{%n{q}, %n{q + 1}}}, [%sp+{byte_off + 8 + 8 * q}];")
 
     def head(nwords):
         """current k <- header fetched by the previous handler; fetch the next header"""
         w("mov.u32 %k, %nk; mov.u32 %op, %nop;")
         w(f"ld.shared.v2.u32 {{%nop, %nk}}, [%sp+{8 * nwords}];")
+        if short_skip:                      # %op = opcode of the NEXT record, known since the previous handler
+            w(f"setp.ge.u32 %plong, %op, {n_short};")
 
     fall_state = [None]
+    short_skip = bool(int(os.environ.get('PIP_SHORT_SKIP', '1')))
+    anchors = bool(int(os.environ.get('PIP_ANCHORS', '0')))
 
     def tail(nwords, preloaded=0, anchor=False):
         preload(8 * nwords, preloaded)
         w(f"add.u32 %sp, %sp, {8 * nwords};")
         if anchor and anchors:
-            # "Uniform anchor".  %op / %nop form ONE live-range web across all handlers (they meet at every indirect
-            # branch).  ptxas either keeps that web in uniform registers -- dispatches become BRXU with the jump-table read
-            # hoisted to the top of the handler -- or in vector registers (BRX R: `branch_resolving` stalls, ncu 0.34
-            # instead of 0.06 cycles per issue, ~8 % of the kernel).  Which one it picks depends on register pressure and
-            # on how many dispatch sites test the opcode with a uniform predicate, like the duplicated ("fall") handlers
-            # do.  The rarely executed handlers (ENTER / LEAVE / MASK: 9 % of the records) can add such sites at the
-            # price of one BRA.U each; for the 2B kernel this is what keeps BRXU once the slim stack has removed the
-            # register pressure that used to force it (and with it 8 R2UR per record): 1.036 instead of 1.075 ms.
             w("setp.ne.u32 %pself, %op, 0x7fffffff; @%pself brx.idx %op, TBL; bra.uni FINISH;")
             return
         if fall_state[0] is not None:
@@ -574,6 +582,7 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
 
     w("ld.shared.u32 %op, [%bufcur];")         # word 0 of the stream: the first opcode
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
+    w(f"setp.ge.u32 %plong, %op, {n_short};")
     preload(0)
     w("brx.idx %op, TBL;")
     # ---- END
@@ -589,11 +598,13 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     async_fetch("%bufoth")
     w("add.u32 %sp, %bufcur, 8;")
     w("ld.shared.v2.u32 {%nop, %nk}, [%sp];")
+    w(f"setp.ge.u32 %plong, %op, {n_short};")
     preload(0)
     w("brx.idx %op, TBL;")
     # ---- ENTER_d  (payload: const in %n0)
-    # slim: a saved level keeps ONE value (v = vc + vd) and its adjoint; x_k is re-read from shared memory when the level
-    # is left (4 instead of 8 registers per level).
+    # slim: the saved level keeps ONE value (v = vc + vd) and its adjoint; x_k is re-read from shared memory when the
+    # level is left (4 instead of 8 registers per level: the kernel sits at the 255-register limit, and whatever does not
+    # fit ptxas parks in uniform registers at the price of two R2UR per value and record)
     for d in range(1, MAX_DEPTH + 1):
         w(f"H{OP_ENTER + d - 1}:")
         head(2)
@@ -682,7 +693,8 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
                     gi += 1
             for p2 in range(q, q + cnt + (cnt & 1), 2):
                 if p2 + 1 < NPRE:
-                    w(f"ld.shared.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [%sp+{8 * nwords + 8 + 8 * p2}];")
+                    pred = "@%plong " if (p2 >= 2 and short_skip) else ""
+                    w(f"{pred}ld.shared.v2.f64 {{%n{p2}, %n{p2 + 1}}}, [%sp+{8 * nwords + 8 + 8 * p2}];")
                     done = p2 + 2
         preload(8 * nwords, done)
         if fused:
@@ -738,7 +750,8 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
             # payload words < 2 + 2 * (js[-1] + 1) are dead now: refill their registers with the next record's words
             dead = 2 + 2 * (js[-1] + 1)
             while done + 2 <= min(dead, NPRE):
-                w(f"ld.shared.v2.f64 {{%n{done}, %n{done + 1}}}, [%sp+{8 * nwords + 8 + 8 * done}];")
+                pred = "@%plong " if (done >= 2 and short_skip) else ""
+                w(f"{pred}ld.shared.v2.f64 {{%n{done}, %n{done + 1}}}, [%sp+{8 * nwords + 8 + 8 * done}];")
                 done += 2
         preload(8 * nwords, done)
         assert not pending
@@ -755,9 +768,9 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
         tail(nwords, NPRE)
 
     for mi, m in enumerate(masks):
-        block_handler(f"H{OP_MASK + mi}", m, False)
+        block_handler(f"H{m_base + mi}", m, False)
     for mi, m in enumerate(masks):
-        op = OP_MASK + nm + mi
+        op = l_base + mi
         copies = fall_copies if op in fall else 1
         # back-to-back copies: every copy but the last falls through into the next one when the next record has the
         # same opcode (runs of equal records are the rule: symmetry-related siblings)
@@ -822,15 +835,19 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
 
 def count_fp64(recs, masks, phases, dual):
     nm = len(masks)
-    t_base = OP_MASK + 2 * nm
-    s_base = t_base + len(phases)
-    d_base = s_base + MAX_DEPTH
+    t_base, s_base, m_base, l_base, d_base = op_bases(nm, len(phases))
     n_fp = 0
     hist = collections.Counter()
     for op, k, payload in recs:
         if op >= d_base:
             n_fp += 2 * (2 * len(masks[dual[op - d_base]]) + 4)
             hist["dual"] += 1
+        elif op >= l_base:
+            n_fp += 2 * len(masks[op - l_base]) + 4
+            hist["leafnode"] += 1
+        elif op >= m_base:
+            n_fp += 2 * len(masks[op - m_base])
+            hist["mask"] += 1
         elif op >= s_base:
             n_fp += 4
             hist["sibling"] += 1
@@ -840,12 +857,6 @@ def count_fp64(recs, masks, phases, dual):
             if p + 1 < len(phases):
                 n_fp += sum(len(o) - 1 for o in phases[p + 1])
             hist["transition"] += 1
-        elif op >= OP_MASK + nm:
-            n_fp += 2 * len(masks[op - OP_MASK - nm]) + 4
-            hist["leafnode"] += 1
-        elif op >= OP_MASK:
-            n_fp += 2 * len(masks[op - OP_MASK])
-            hist["mask"] += 1
         elif op == OP_NEXT:
             pass
         elif op >= OP_LEAVE:
@@ -858,7 +869,7 @@ def count_fp64(recs, masks, phases, dual):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_weight=40, fall=4, npre=8, fall_copies=2,
-             dual_max=0, group=4, maxnreg=0, slim=False, anchors=False):
+             dual_max=0, group=4, maxnreg=0, slim=False):
     """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual)."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
@@ -867,7 +878,7 @@ def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_
     recs, masks, phases, dual = serialise(name, tab, sym, skeleton_weight, dual_max)
     nm = len(masks)
     runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
-    lo, hi = OP_MASK + nm, OP_MASK + 2 * nm
+    lo, hi = op_bases(nm, len(phases))[3:5]
     fall_ops = tuple(sorted(op for op, c in runs.items() if fall and c >= fall and lo <= op < hi))
     words = pack(recs, chunk)
     n_fp, hist = count_fp64(recs, masks, phases, dual)
@@ -880,7 +891,7 @@ def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_
     lines.append("};")
     entry = f"{name}_eval"
     kl, smem = kernel_ptx(name, entry, symbol, masks, nv, phases, dual, block, min_blocks, piece, fall_ops, npre,
-                          fall_copies, group, maxnreg, slim, anchors)
+                          fall_copies, group, maxnreg, slim)
     lines += [""] + kl
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, f"{name}_eval.ptx"), "w") as fh:
@@ -907,7 +918,6 @@ def main():
         ap.add_argument(f"--dual{two}", type=int, default=d[4], help="DUAL records for handlers of at most N slots")
         ap.add_argument(f"--maxnreg{two}", type=int, default=0, help="register cap (0: none); see kernel_ptx")
         ap.add_argument(f"--slim{two}", type=int, default=0, help="1: saved tree levels keep 2 doubles instead of 4")
-        ap.add_argument(f"--anchors{two}", type=int, default=0, help="1: uniform anchors in the rare handlers (see tail())")
     ap.add_argument("--skeleton-weight", type=int, default=40)
     ap.add_argument("--fall", type=int, default=4, help="duplicate leaf handlers that follow themselves at least N times")
     ap.add_argument("--fall-copies", type=int, default=2)
@@ -921,7 +931,7 @@ def main():
         meta, *_ = generate(name, args.out, getattr(args, "block" + t), args.min_blocks, getattr(args, "piece" + t),
                             getattr(args, "sym" + t), args.skeleton_weight, args.fall, getattr(args, "npre" + t),
                             args.fall_copies, getattr(args, "dual" + t), args.group, getattr(args, "maxnreg" + t),
-                            bool(getattr(args, "slim" + t)), bool(getattr(args, "anchors" + t)))
+                            bool(getattr(args, "slim" + t)))
         print({k: v for k, v in meta.items() if k != "phases"})
 
 
