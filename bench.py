@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--ref-dimers", type=int, default=20000)
     ap.add_argument("--ref-trimers", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nve-steps", type=int, default=10, help="steps of the on-device NVE sweep line (0: skip; N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -379,6 +380,36 @@ def main():
                   "ms_of_a_step_with_rebalance": slow,
                   "amortised_ms_per_step": (ms / args.steps) + ((slow - ms / args.steps) / every if slow and every else 0.0)}
 
+    # ---- NVE sweep (BASELINE config 5), single GPU: the on-device velocity-Verlet loop of the C ABI (mbpol_nve_run), lists
+    # rebuilt every step like the reference, then with a 0.05 nm Verlet skin; 298 K velocities, dt 0.2 fs.  Positions,
+    # velocities, forces and energies never leave HBM inside the loop.
+    nve_line = None
+    if world == 1 and args.nve_steps > 0:
+        from mbpol_openmm_plugin_b200 import nve
+        ctx.engine.set_timing(False)
+        m = torch.as_tensor(nve.masses(n).reshape(-1)).to(dev)
+        nve_line = {"steps": args.nve_steps, "dt_fs": 0.2, "temperature_K": 298.0}
+        for tag, skin in (("rebuild_every_step", 0.0), ("skin_0.05nm", 0.05)):
+            ctx.engine.set_skin(skin)
+            p = pos_dev.clone()
+            v = torch.as_tensor(nve.maxwell_boltzmann(n, 298.0)).to(dev)
+            nve.run_device(ctx, p, v, m, 2)                                   # warm-up (and the first skin build)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            rb0 = ctx.engine.stats()["n_row_builds"]
+            e0.record()
+            log = nve.run_device(ctx, p, v, m, args.nve_steps)
+            e1.record()
+            torch.cuda.synchronize()
+            evals = args.nve_steps + 1                     # the run evaluates the forces of the start once more
+            st = ctx.engine.stats()
+            nve_line[tag] = {"ms_per_step": e0.elapsed_time(e1) / evals,
+                             "water_steps_per_s": n * evals / (e0.elapsed_time(e1) * 1e-3),
+                             "row_builds": int(st["n_row_builds"] - rb0), "force_evaluations": evals,
+                             "energy_drift_kJ_mol": float(log[-1].sum() - log[0].sum())}
+        ctx.engine.set_skin(0.0)
+        ctx.engine.set_timing(True)
+
     if rank == 0:
         n_pairs, n_trips = totals if totals else (int(stats["n_pairs"]), int(stats["n_triplets"]))
         value = n * args.steps / (ms * 1e-3)
@@ -438,6 +469,8 @@ def main():
             line["parity_vs_single"] = parity
         if repart is not None:
             line["repartition"] = repart
+        if nve_line is not None:
+            line["nve"] = nve_line
         if world == 1 and not args.no_cpu_baseline:
             v, desc, kind, info = cpu_reference_rate(pos_mol, box, args.ref_dimers, args.ref_trimers)
             line["cpu_baseline"] = {"value": v, "unit": "water-steps/s", "cores": 1, "kind": kind, "sample": desc,
