@@ -66,11 +66,12 @@ typedef struct mbpol_config {
 
 /* counters of the last mbpol_eval call */
 typedef struct mbpol_stats {
-    int64_t n_pairs;        /* listed dimers  (O-O <= cutoff_2b)                        */
-    int64_t n_triplets;     /* listed trimers (reference chain set)    */
+    int64_t n_pairs;        /* listed dimers  (O-O <= cutoff_2b); -1 when the lists of this evaluation were SLICED (multi-  */
+    int64_t n_triplets;     /* GPU: only this rank's tuples exist, the box-wide totals are unknown); trimers: chain set      */
     int64_t n_pairs_owned;  /* dimers / trimers evaluated by THIS context (owner range)  */
     int64_t n_triplets_owned;
-    float   ms_lists, ms_2b, ms_3b, ms_reduce;   /* device time of the stages (CUDA events), 0 if timing disabled */
+    float   ms_lists, ms_2b, ms_3b, ms_reduce;   /* device time of the stages (CUDA events), 0 if timing disabled; when the two
+                                                    forces disagree on periodicity (two list builds) they describe the 3B pass */
     float   ms_pip_2b, ms_pip_3b;                /* the polynomial kernels alone (the roofline kernels)             */
     int64_t n_launches;     /* kernels launched by the last mbpol_eval (library-internal CUB passes counted once each) */
     float   ms_bcast, ms_comm_reduce;            /* mbpol_eval_distributed: the two collectives (CUDA events)        */

@@ -623,3 +623,44 @@ def test_verlet_skin_lists_equal_the_rebuilt_lists_at_every_step():
     sa, sb = a.engine.stats(), b.engine.stats()
     assert sa["n_row_builds"] == 12 and not sa["lists_reused"]
     assert reused >= 8 and sb["n_row_builds"] <= 4
+
+
+def test_sliced_build_that_falls_back_on_some_ranks_keeps_the_owner_ranges():
+    """A sliced build falls back to full lists on exactly the ranks whose rows overflow the fixed stride (here: a 1.3 nm
+    2B cutoff, ~300 neighbours; the high-index ranks overflow, rank 0 with few lower-index neighbours may not).  The owner
+    ranges and the refresh schedule must not move on those ranks alone: at every step of a random walk the partial results
+    of the ranks must still add up to the unpartitioned result (tuples neither dropped nor counted twice)."""
+    import torch
+    from mbpol_openmm_plugin_b200.systems import synthetic_box
+    pos, box = synthetic_box(2)
+    n = len(pos)
+    world = 3
+    full = make_context(n, box, True, cut2=1.3)
+    ranks = [make_context(n, box, True, cut2=1.3, rank=r, world=world) for r in range(world)]
+    rng = np.random.default_rng(9)
+    p = pos.reshape(-1, 3).copy()
+    sliced_seen = fallback_seen = 0
+    for step in range(5):
+        if step:
+            p += np.repeat(rng.normal(scale=0.01, size=(n, 3)), 3, axis=0)
+        t = torch.as_tensor(p).cuda()
+        full.setPositions(t)
+        e_full = full.getPotentialEnergy()
+        f_full = full.getForces()
+        e_sum, f_sum, owned2, owned3 = 0.0, torch.zeros_like(f_full), 0, 0
+        for ctx in ranks:
+            ctx.setPositions(t)
+            e_sum += ctx.getPotentialEnergy()
+            f_sum += ctx.getForces()
+            st = ctx.engine.stats()
+            owned2 += st["n_pairs_owned"]
+            owned3 += st["n_triplets_owned"]
+            if step:
+                sliced_seen += st["lists_sliced"]
+                fallback_seen += not st["lists_sliced"]
+        stf = full.engine.stats()
+        assert (owned2, owned3) == (stf["n_pairs"], stf["n_triplets"])             # a partition of the tuples, every step
+        assert abs(e_sum - e_full) <= 1e-10 * abs(e_full)
+        assert (f_sum - f_full).abs().max().item() < 1e-8
+    assert fallback_seen > 0                                     # the situation of the test did occur
+    assert all(c.engine.stats()["n_repartitions"] == 1 for c in ranks)          # nobody rebalanced on its own
