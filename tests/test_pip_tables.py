@@ -80,7 +80,8 @@ def test_command_stream_matches_table(name, opts, tmp_path):
 @pytest.mark.parametrize("opts", [
     {"K": (20, 12), "npre": 16, "piece": 16, "ahead": 1, "anchors": True},          # shipped (build.py MSYM_ARGS)
     {"K": (12, 12), "npre": 8, "piece": 16},
-    {"K": (12, 12), "npre": 12, "piece": 16, "swap_phase": True}])                  # swap phase: 6 + 3 x 2 contexts
+    {"K": (12, 12), "npre": 12, "piece": 16, "mode": "swap"},                       # swap phase: 6 + 3 x 2 contexts
+    {"K": (16, 16), "npre": 16, "piece": 16, "mode": "pairs", "anchors": True}])    # pair-sum family: 6 + 6 contexts
 def test_molecule_symmetrised_stream_matches_table(opts, tmp_path):
     """tools/gen_msym.py: P(x) = sum over the six molecule relabellings of Q(sigma x); the python interpreter of the packed
     stream (the records the 3B kernel executes, six contexts per record) vs the monomial definition of P"""

@@ -155,32 +155,40 @@ def expand(node, prefix=()):
 
 
 class Phase:
-    """swap set S (indices into swap_perms), pass permutation tau, context permutations rho_c (identity first).
-    Register slot j (lowest variable of an S-orbit) holds sum_{i in orbit_j} x[tau[i]]; context c reads slot
-    pi_c(j) = slot of rho_c(orbit_j) and its node variable is tau[rho_c[k]]."""
+    """slot family, pass permutation tau, context permutations rho_c (identity first).
+    Register slot `sid[q]` holds sum_{i in orbs[q]} x[tau[i]]; context c reads slot pi_c(j) = the slot whose member set
+    is rho_c(members of j) -- the family must be closed under the contexts -- and its node variable is tau[rho_c[k]].
+    Member sets may overlap (a variable sits in the pair sums of two swaps): the gradient of a slot goes to all its
+    members, the sums over slots add up."""
 
-    def __init__(self, nv, swaps, S, tau, ctx, cls):
-        self.S, self.tau, self.ctx, self.cls = S, tau, ctx, cls
-        self.orbs = gi._orbits(nv, [swaps[i] for i in S])
-        self.slot_of = {}
-        for o in self.orbs:
-            for i in o:
-                self.slot_of[i] = o[0]
-        self.pi = []
-        for rho in ctx:
-            pm = {}
-            for o in self.orbs:
-                im = {self.slot_of[rho[i]] for i in o}
-                assert len(im) == 1, "context does not normalise the swap set"
-                pm[o[0]] = im.pop()
-            self.pi.append(pm)
+    def __init__(self, nv, slots, tau, ctx, cls):
+        self.tau, self.ctx, self.cls = tau, ctx, cls
+        self.sid = [j for j, _ in slots]
+        self.orbs = [list(m) for _, m in slots]
+        key = {frozenset(m): j for j, m in slots}
+        assert len(key) == len(slots) and len(set(self.sid)) == len(slots) and max(self.sid) < nv
+        self.pi = [{j: key[frozenset(rho[i] for i in m)] for j, m in slots} for rho in ctx]
         self.kmap = [compose(tau, rho) for rho in ctx]
 
 
-def symmetrise(name, swap_phase=False):
-    """-> (root of the tree of Q, nv, phase classes, phases, node -> class index).
-    Class 0: no swap, all molecule permutations as contexts.  With swap_phase (3B): class 1 = swap a, contexts e and
-    (bc), three passes."""
+PAIR_SINGLES = {"pip3b": [21, 23, 25, 27, 29, 31, 22, 24, 26, 28, 30, 32, 33, 34, 35]}     # O-H and O-O between molecules
+
+
+def pair_slots(name, nv, swaps):
+    """the mixed family of `pairs` mode: the 21 hydrogen-swap pair sums x_v + x_swap(v) of all three swaps (closed under
+    the molecule relabellings, so ALL six contexts can use them) + the singles that leaf nodes with pairs need most,
+    filling the same 36 registers"""
+    pairs = sorted({tuple(sorted((v, s[v]))) for s in swaps for v in range(nv) if s[v] != v})
+    members = [list(p) for p in pairs] + [[v] for v in PAIR_SINGLES[name]]
+    assert len(members) <= nv
+    return [(q, m) for q, m in enumerate(members)]
+
+
+def symmetrise(name, mode="single"):
+    """-> (root of the tree of Q, nv, phases, molecule permutations).
+    mode single: one phase, 36 single-variable slots, all molecule permutations as contexts.
+         swap  : + class 1 = orbit sums of swap a, contexts e and (bc), three passes (measured: slower; kept for the record)
+         pairs : + class 1 = pair sums of all swaps + 15 singles, all contexts (see pair_slots)"""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
     coef = tab["coef"]
@@ -193,7 +201,7 @@ def symmetrise(name, swap_phase=False):
     sites, _ = gi._sites(name)
     ha = [any(s.startswith("Ha") for s in p) for p in sites]
     orbs = s_orbits(monos, coef, perms)
-    root = build_free(orbs, None, (lambda v: 0 if ha[v] else 1) if swap_phase else (lambda v: 0))
+    root = build_free(orbs, None, (lambda v: 0 if ha[v] else 1) if mode == "swap" else (lambda v: 0))
     # exactness of the representation: sum over the images of Q == P, term by term
     acc = collections.defaultdict(float)
     for m, val in expand(root).items():
@@ -202,37 +210,67 @@ def symmetrise(name, swap_phase=False):
     assert set(acc) == set(monos)
     assert max(abs(acc[m] - coef[c]) / abs(coef[c]) for m, c in monos.items()) < 1e-15
     ident = list(range(nv))
-    phases = [Phase(nv, swaps, (), ident, perms, 0)]
-    if swap_phase:
+    phases = [Phase(nv, [(v, [v]) for v in range(nv)], ident, perms, 0)]
+    if mode == "swap":
         assert name == "pip3b"
-        keys = list(mp)
         bc, ab, ac = mp[("a", "c", "b")], mp[("b", "a", "c")], mp[("c", "b", "a")]
+        slots = [(o[0], o) for o in gi._orbits(nv, [swaps[0]])]
         for tau in (ident, ab, ac):
-            phases.append(Phase(nv, swaps, (0,), tau, [ident, bc], 1))
+            phases.append(Phase(nv, slots, tau, [ident, bc], 1))
         cover = sorted(tuple(compose(ph.tau, rho)) for ph in phases[1:] for rho in ph.ctx)
-        assert cover == sorted(tuple(p) for p in perms), keys
+        assert cover == sorted(tuple(p) for p in perms)
+    elif mode == "pairs":
+        phases.append(Phase(nv, pair_slots(name, nv, swaps), ident, perms, 1))
+    else:
+        assert mode == "single"
     return root, nv, phases, perms
 
 
-def classify(root, phases):
-    """class of every leaf-bearing node: the class (of those offered) that needs fewest slots; -> {id(node): (cls, need)}
-    need = {slot: value}"""
+def classify(root, phases, mode, overhead=3):
+    """-> {id(node): [(class, need = {slot: value}, constant or None), ...]} for every node with leaves or a constant.
+    single: everything in class 0.  swap: the class that needs fewest slots.  pairs: a node is evaluated in class 0, in
+    class 1 or SPLIT between them (its linear form is a sum of two), whatever costs least with `overhead` slots per record."""
     by_cls = {}
     for ph in phases:
         by_cls.setdefault(ph.cls, ph)
     out = {}
 
+    def express(n, ph):
+        """greedy cover of the leaves with the slots of ph: pair slots where both members carry the same coefficient,
+        single slots otherwise; -> (need, leaves left over)"""
+        left, need = dict(n.leaves), {}
+        for j, m in zip(ph.sid, ph.orbs):
+            if len(m) > 1 and all(v in left for v in m) and len({left[v] for v in m}) == 1:
+                need[j] = left[m[0]]
+                for v in m:
+                    del left[v]
+        for j, m in zip(ph.sid, ph.orbs):
+            if len(m) == 1 and m[0] in left:
+                need[j] = left.pop(m[0])
+        return need, left
+
     def walk(n):
         if n.leaves or n.const is not None:
-            best = None
-            for cls, ph in by_cls.items():
-                if all(len({n.leaves.get(v) for v in o}) == 1 for o in ph.orbs):
-                    need = {o[0]: n.leaves[o[0]] for o in ph.orbs if o[0] in n.leaves}
-                    # weight: slots x contexts-per-coefficient-load is what the FP64 pipe sees; all classes run every
-                    # node |S| times, so the slot count decides
-                    if best is None or len(need) < len(best[1]):
-                        best = (cls, need)
-            out[id(n)] = best
+            full = {v: c for v, c in n.leaves.items()}
+            if mode == "single":
+                out[id(n)] = [(0, full, n.const)]
+            elif mode == "swap":
+                best = (0, full)
+                need, left = express(n, by_cls[1])
+                if not left and len(need) < len(full):
+                    best = (1, need)
+                out[id(n)] = [(best[0], best[1], n.const)]
+            else:
+                need, left = express(n, by_cls[1])
+                c0 = len(full) + overhead
+                c1 = len(need) + overhead if not left else 1 << 30
+                c2 = len(need) + len(left) + 2 * overhead if need and left else 1 << 30
+                if c0 <= min(c1, c2):
+                    out[id(n)] = [(0, full, n.const)]
+                elif c1 <= c2:
+                    out[id(n)] = [(1, need, n.const)]
+                else:
+                    out[id(n)] = [(1, need, n.const), (0, left, None)]
         for k in n.kids:
             walk(k)
     walk(root)
@@ -247,16 +285,16 @@ def op_layout(phases, handlers=()):
     return ncls, op_trans, op_leaf0, op_leaf0 + len(handlers)
 
 
-def serialise(name, K=(12, 12), swap_phase=False):
-    """-> (records, handlers, phases, nv).  records: (op, [node variable per context], payload doubles); handlers: list of
-    (class, slot tuple) in opcode order (LEAF_h = op_leaf0 + h)."""
-    root, nv, phases, perms = symmetrise(name, swap_phase)
-    cls = classify(root, phases)
+def serialise(name, K=(12, 12), mode="single", overhead=3):
+    """-> (records, handlers, phases, nv).  records: (op, [node variable per context], payload doubles, [parent's node
+    variables: LEAVE_2 only]); handlers: list of (class, slot tuple) in opcode order (LEAF_h = op_leaf0 + h)."""
+    root, nv, phases, perms = symmetrise(name, mode)
+    cls = classify(root, phases, mode, overhead)
     ncls, op_trans, op_leaf0, _ = op_layout(phases)
     bits = lambda need: sum(1 << j for j in need)  # noqa: E731
     libs, pick = [], []
     for c in range(ncls):
-        req = collections.Counter(bits(need) for cc, need in cls.values() if cc == c)
+        req = collections.Counter(bits(need) for parts in cls.values() for cc, need, _ in parts if cc == c)
         lib = gi.merge_library(req, K[c]) if req else []
         pk = {}
         for b in req:
@@ -272,7 +310,7 @@ def serialise(name, K=(12, 12), swap_phase=False):
     has = {}
 
     def mark(n):
-        s = {cls[id(n)][0]} if id(n) in cls else set()
+        s = {c for c, _, _ in cls.get(id(n), [])}
         for k in n.kids:
             s |= mark(k)
         has[id(n)] = s
@@ -283,29 +321,32 @@ def serialise(name, K=(12, 12), swap_phase=False):
         def ks(var):
             return [km[var] for km in ph.kmap]
 
-        def leaf_rec(n):
-            c, need = cls[id(n)]
-            i = hid[(c, pick[c][bits(need)])]
-            pl = [n.const if n.const is not None else 0.0] + [need.get(j, 0.0) for j in handlers[i][1]]
-            recs.append((op_leaf0 + i, ks(n.var), pl, []))
+        def own_part(n):
+            for part in cls.get(id(n), []):
+                if part[0] == ph.cls:
+                    return part
+            return None
 
         def emit(n, depth, parent=None):
-            own = id(n) in cls and cls[id(n)][0] == ph.cls
+            part = own_part(n)
             kids = [k for k in n.kids if ph.cls in has[id(k)]]
             if depth == 0:
                 assert id(n) not in cls, "constants / leaves at the root: not needed by pip3b"
             else:
-                if own:
-                    leaf_rec(n)
+                if part:
+                    c, need, const = part
+                    i = hid[(c, pick[c][bits(need)])]
+                    pl = [const if const is not None else 0.0] + [need.get(j, 0.0) for j in handlers[i][1]]
+                    recs.append((op_leaf0 + i, ks(n.var), pl, []))
                 if not kids:
                     return
                 assert depth <= MAX_ENTER_DEPTH
                 recs.append((OP_SKEL + 4 * ph.cls + depth - 1, ks(n.var), [], []))
 
             def order(k):           # childless kids grouped by handler: equal records adjacent
-                if id(k) in cls and not any(ph.cls in has[id(q)] for q in k.kids):
-                    c, need = cls[id(k)]
-                    return (0, hid[(c, pick[c][bits(need)])])
+                part = own_part(k)
+                if part and not any(ph.cls in has[id(q)] for q in k.kids):
+                    return (0, hid[(part[0], pick[part[0]][bits(part[1])])])
                 return (1, 0)
             for k in sorted(kids, key=order):
                 emit(k, depth + 1, n)
@@ -386,7 +427,7 @@ def interpret(name, words, x, chunk_bytes, handlers, phases, nt, kvars):
     ncls, op_trans, op_leaf0, _ = op_layout(phases, handlers)
 
     def load_phase(ph):
-        return {o[0]: sum(x[ph.tau[i]] for i in o) for o in ph.orbs}, {o[0]: 0.0 for o in ph.orbs}
+        return {j: sum(x[ph.tau[i]] for i in o) for j, o in zip(ph.sid, ph.orbs)}, {j: 0.0 for j in ph.sid}
     p = 0
     ph = phases[0]
     R, Gr = load_phase(ph)
@@ -430,9 +471,9 @@ def interpret(name, words, x, chunk_bytes, handlers, phases, nt, kvars):
             pc += 2 * H if kind == 3 else H
         elif op < op_leaf0:                                  # TRANS_p
             assert op - op_trans == p
-            for o in ph.orbs:
+            for j, o in zip(ph.sid, ph.orbs):
                 for i in o:
-                    g[ph.tau[i]] += Gr[o[0]]
+                    g[ph.tau[i]] += Gr[j]
             vr += sum(v)
             v = [0.0] * C
             p += 1
@@ -556,17 +597,22 @@ def kernel_ptx(name, entry, stream, handlers, nv, phases, kvars, block=256, piec
         w(f"st.shared.f64 [%sx+{r}], %w; st.shared.f64 [%sx+{SGA[0] + r}], %zero; st.shared.f64 [%sx+{SGA[1] + r}], %zero;")
     w("mov.f64 %vr, %zero;")
 
-    def load_phase(ph):
-        for o in ph.orbs:
-            j = o[0]
-            xaddr(ph.tau[o[0]])
-            w(f"ld.global.nc.f64 %x{j}, [%pa]; mov.f64 %g{j}, %zero;")
-            for i in o[1:]:
+    def load_phase(ph, first=False):
+        def ldx(dst, i):                 # the first phase loads from global memory, later ones from the shared copy
+            if first:
                 xaddr(ph.tau[i])
-                w(f"ld.global.nc.f64 %w, [%pa]; add.rn.f64 %x{j}, %x{j}, %w;")
+                w(f"ld.global.nc.f64 {dst}, [%pa];")
+            else:
+                w(f"ld.shared.f64 {dst}, [%sx+{kidx[ph.tau[i]] * NT * 8}];")
+        for j, o in zip(ph.sid, ph.orbs):
+            ldx(f"%x{j}", o[0])
+            w(f"mov.f64 %g{j}, %zero;")
+            for i in o[1:]:
+                ldx("%w", i)
+                w(f"add.rn.f64 %x{j}, %x{j}, %w;")
         for c in range(len(ph.ctx)):
             w(f"mov.f64 %v{c}, %zero; mov.f64 %a{c}, %one;")
-    load_phase(phases[0])
+    load_phase(phases[0], True)
     w("bar.sync 0;")
     w("add.u32 %sp, %bufcur, 16;")
     w("TBL: .branchtargets " + ", ".join(f"H{i}" for i in range(n_ops)) + ";")
@@ -668,10 +714,10 @@ def kernel_ptx(name, entry, stream, handlers, nv, phases, kvars, block=256, piec
         w("mov.u32 %op, %nop;")
         nxt = phases[p + 1] if p + 1 < len(phases) else None
         load_hdr(HB, len(nxt.ctx) if nxt else 1)
-        for o in ph.orbs:
+        for j, o in zip(ph.sid, ph.orbs):
             for i in o:
                 r = SGA[0] + kidx[ph.tau[i]] * NT * 8
-                w(f"ld.shared.f64 %gk, [%sx+{r}]; add.rn.f64 %gk, %gk, %g{o[0]}; st.shared.f64 [%sx+{r}], %gk;")
+                w(f"ld.shared.f64 %gk, [%sx+{r}]; add.rn.f64 %gk, %gk, %g{j}; st.shared.f64 [%sx+{r}], %gk;")
         for c in range(len(ph.ctx)):
             w(f"add.rn.f64 %vr, %vr, %v{c};")
         if nxt:
@@ -781,8 +827,9 @@ def count_fp64(recs, handlers, phases):
     return n_fp, hist
 
 
-def generate(name, out_dir, block=256, piece=64, K=(12, 12), npre=8, swap_phase=False, ahead=2, maxnreg=0, anchors=False):
-    recs, handlers, phases, nv = serialise(name, K, swap_phase)
+def generate(name, out_dir, block=256, piece=64, K=(12, 12), npre=8, mode="single", ahead=2, maxnreg=0, anchors=False,
+             overhead=3):
+    recs, handlers, phases, nv = serialise(name, K, mode, overhead)
     cmax = max(len(ph.ctx) for ph in phases)
     chunk = block * piece
     kvars = node_vars(recs)
@@ -820,12 +867,13 @@ def main():
     ap.add_argument("--k1", type=int, default=12, help="leaf handlers of class 1 (swap phase)")
     ap.add_argument("--npre", type=int, default=8)
     ap.add_argument("--ahead", type=int, default=2)
-    ap.add_argument("--swap-phase", type=int, default=0)
+    ap.add_argument("--mode", default="single", help="single | swap | pairs (see symmetrise)")
+    ap.add_argument("--overhead", type=int, default=3, help="pairs mode: cost of a record in slots (node split decision)")
     ap.add_argument("--maxnreg", type=int, default=0)
     ap.add_argument("--anchors", type=int, default=0)
     args = ap.parse_args()
-    meta, *_ = generate(args.only, args.out, args.block, args.piece, (args.k0, args.k1), args.npre, bool(args.swap_phase),
-                        args.ahead, args.maxnreg, bool(args.anchors))
+    meta, *_ = generate(args.only, args.out, args.block, args.piece, (args.k0, args.k1), args.npre, args.mode,
+                        args.ahead, args.maxnreg, bool(args.anchors), args.overhead)
     print(meta)
 
 
