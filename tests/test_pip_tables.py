@@ -78,7 +78,8 @@ def test_command_stream_matches_table(name, opts, tmp_path):
 
 
 @pytest.mark.parametrize("opts", [
-    {"K": (20, 12), "npre": 16, "piece": 16, "ahead": 1, "anchors": True},          # shipped (build.py MSYM_ARGS)
+    {"K": (24,), "npre": 16, "piece": 16, "ahead": 1, "anchors": True, "mode": "basis"},   # shipped (build.py MSYM_ARGS)
+    {"K": (20, 12), "npre": 16, "piece": 16, "ahead": 1, "anchors": True},          # single-variable slots
     {"K": (12, 12), "npre": 8, "piece": 16},
     {"K": (12, 12), "npre": 12, "piece": 16, "mode": "swap"},                       # swap phase: 6 + 3 x 2 contexts
     {"K": (16, 16), "npre": 16, "piece": 16, "mode": "pairs", "anchors": True}])    # pair-sum family: 6 + 6 contexts
@@ -99,6 +100,8 @@ def test_molecule_symmetrised_stream_matches_table(opts, tmp_path):
     assert meta["smem_bytes"] <= 227 * 1024
     assert meta["contexts"][0] == 6 and sum(meta["contexts"]) in (6, 12)
     assert meta["records"]["leaf"] < 800                            # 2,050 leaf nodes before the symmetrisation
+    if opts.get("mode") == "basis":
+        assert meta["fp64_instr"] < 70000                           # 78,528 with single-variable slots
 
 
 @pytest.mark.parametrize("name", ["pip2b", "pip3b"])
@@ -122,7 +125,7 @@ def test_shipped_generator_settings_are_tested():
     from mbpol_openmm_plugin_b200 import build
     a = build.GEN_ARGS
     assert (a["sym2"], a["block2"], a["piece2"], a["npre2"], a["dual2"], a["slim2"], a["anchors2"]) == (12, 384, 32, 4, 4, 1, 1)
-    assert build.MSYM_ARGS == {"k0": 20, "piece": 16, "npre": 16, "ahead": 1, "anchors": 1}
+    assert build.MSYM_ARGS == {"mode": "basis", "k0": 24, "piece": 16, "npre": 16, "ahead": 1, "anchors": 1}
 
 
 @pytest.mark.parametrize("name", ["pip2b", "pip3b"])

@@ -184,6 +184,45 @@ def pair_slots(name, nv, swaps):
     return [(q, m) for q, m in enumerate(members)]
 
 
+def adapted_basis(name, nv, swaps, keep="2"):
+    """Symmetry-adapted slot family of `basis` mode: an invertible 0/1 change of basis of the nv variables, block by block
+    over the orbits of the hydrogen-swap group, closed under the molecule relabellings:
+        orbit {v}                      -> v
+        orbit {v1, v2} (one swap)      -> v1 + v2,  v2      (O-H inside a molecule; O-H between molecules stays v1, v2:
+                                                              measured, the change of basis costs slots there)
+        orbit {w11, w12, w21, w22}     -> sum of all four,  w21 + w22,  w12 + w22,  w22       (H-H between two molecules)
+    A node's linear form sum_v c_v x_v is rewritten in this basis (the inverse has entries 0, +-1, so the new coefficients
+    are sums / differences of the old ones): leaves that are symmetric under a swap collapse onto the sum slots -- the
+    saving of the orbit-sum phases of gen_interp.py, for all three swaps at once, in the SAME 36 registers and for all six
+    contexts; a lone leaf on a "first" member costs up to four slots instead of one.  3B: 4,166 slots instead of 5,326
+    (all orientations of the three block types were tried: 4,166 ... 5,452).
+    The register of a slot holds the sum of its members; its gradient is added to every member at the end."""
+    sites, _ = gi._sites(name)
+
+    def hidx(v):
+        return tuple(t[-1] if t[0] in "HX" else "0" for t in sites[v])
+    rows = []
+    for o in gi._orbits(nv, swaps):
+        if len(o) == 1:
+            rows.append(o)
+        elif len(o) == 2:
+            (p1, q1) = sites[o[0]]
+            if p1[1] != q1[1]:                           # sites of two molecules: O-H between molecules
+                rows += [[o[0]], [o[1]]]
+            else:
+                rows += [o, [max(o, key=hidx) if keep == "2" else min(o, key=hidx)]]
+        else:
+            assert len(o) == 4
+            ids = {v: hidx(v) for v in o}
+            moving = [q for q in range(2) if len({ids[v][q] for v in o}) == 2]
+            assert len(moving) == 2
+            a, b = moving
+            rows += [o, [v for v in o if ids[v][a] == keep], [v for v in o if ids[v][b] == keep],
+                     [v for v in o if ids[v][a] == keep and ids[v][b] == keep]]
+    assert len(rows) == nv
+    return [(q, sorted(m)) for q, m in enumerate(rows)]
+
+
 def symmetrise(name, mode="single"):
     """-> (root of the tree of Q, nv, phases, molecule permutations).
     mode single: one phase, 36 single-variable slots, all molecule permutations as contexts.
@@ -210,6 +249,9 @@ def symmetrise(name, mode="single"):
     assert set(acc) == set(monos)
     assert max(abs(acc[m] - coef[c]) / abs(coef[c]) for m, c in monos.items()) < 1e-15
     ident = list(range(nv))
+    if mode.startswith("basis"):
+        phases = [Phase(nv, adapted_basis(name, nv, swaps, mode[5:] or "2"), ident, perms, 0)]
+        return root, nv, phases, perms
     phases = [Phase(nv, [(v, [v]) for v in range(nv)], ident, perms, 0)]
     if mode == "swap":
         assert name == "pip3b"
@@ -249,10 +291,25 @@ def classify(root, phases, mode, overhead=3):
                 need[j] = left.pop(m[0])
         return need, left
 
+    if mode.startswith("basis"):
+        ph = by_cls[0]
+        nv = len(ph.sid)
+        B = np.zeros((nv, nv))
+        for q, m in zip(ph.sid, ph.orbs):
+            B[q, m] = 1.0
+        BinvT = np.rint(np.linalg.inv(B)).T                # entries 0, +-1: sum_v c_v x_v = sum_q (B^-T c)_q (B x)_q
+        assert np.array_equal(BinvT.T @ B, np.eye(nv))
+
     def walk(n):
         if n.leaves or n.const is not None:
             full = {v: c for v, c in n.leaves.items()}
-            if mode == "single":
+            if mode.startswith("basis"):
+                c = np.zeros(nv)
+                for v, val in n.leaves.items():
+                    c[v] = val
+                cp = BinvT @ c
+                out[id(n)] = [(0, {q: float(cp[q]) for q in range(nv) if cp[q] != 0.0}, n.const)]
+            elif mode == "single":
                 out[id(n)] = [(0, full, n.const)]
             elif mode == "swap":
                 best = (0, full)
