@@ -49,6 +49,8 @@ def test_table_reproduces_reference_polynomial_values(name):
     ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 16}),
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 13}),
     ("pip2b", {"sym": 12, "npre": 4, "piece": 32, "block": 384, "dual_max": 4, "slim": True, "anchors": True}),
+    ("pip2b", {"sym": 20, "npre": 4, "piece": 32, "block": 384, "dual_max": 4, "slim": True, "anchors": True, "basis": True}),
+    ("pip3b", {"sym": 28, "npre": 8, "piece": 64, "dual_max": 9, "basis": True}),
     ("pip3b", {"sym": 28, "npre": 8, "piece": 64, "dual_max": 9}),     # (the 3B evaluator of round 1 / 2: kept, not shipped)
     ("pip3b", {"sym": 32, "npre": 8, "piece": 64, "dual_max": 32, "group": 2}),
     ("pip2b", {"sym": 16, "skeleton_weight": 0}), ("pip3b", {"sym": 24, "skeleton_weight": 0, "fall": 0})])
@@ -69,9 +71,16 @@ def test_command_stream_matches_table(name, opts, tmp_path):
     assert meta["smem_bytes"] <= 227 * 1024
     # every variable belongs to exactly one orbit of every phase; phase 0 is the identity
     nv = int(t["n_vars"])
-    assert meta["phases"][0] == [[j] for j in range(nv)]
-    for orbs in meta["phases"]:
-        assert sorted(v for o in orbs for v in o) == list(range(nv))
+    if opts.get("basis"):       # ONE phase in the symmetry-adapted basis: nv rows with distinct lowest variables, invertible
+        assert len(meta["phases"]) == 1 and sorted(o[0] for o in meta["phases"][0]) == list(range(nv))
+        B = np.zeros((nv, nv))
+        for q, o in enumerate(meta["phases"][0]):
+            B[q, o] = 1.0
+        assert abs(abs(np.linalg.det(B)) - 1.0) < 1e-9
+    else:
+        assert meta["phases"][0] == [[j] for j in range(nv)]
+        for orbs in meta["phases"]:
+            assert sorted(v for o in orbs for v in o) == list(range(nv))
     assert meta["fp64_instr"] < {"pip2b": 24000, "pip3b": 67500}[name]     # vs 30,180 / 79,182 without symmetry
     if opts.get("dual_max"):
         assert meta["records"]["dual"] > 100 and meta["dual"]            # pairs of sibling leaf nodes were found and fused
@@ -124,7 +133,8 @@ def test_shipped_generator_settings_are_tested():
     """whatever build.py ships must be one of the configurations the stream tests above interpret"""
     from mbpol_openmm_plugin_b200 import build
     a = build.GEN_ARGS
-    assert (a["sym2"], a["block2"], a["piece2"], a["npre2"], a["dual2"], a["slim2"], a["anchors2"]) == (12, 384, 32, 4, 4, 1, 1)
+    assert (a["sym2"], a["block2"], a["piece2"], a["npre2"], a["dual2"], a["slim2"], a["anchors2"], a["basis2"]) == \
+        (20, 384, 32, 4, 4, 1, 1, 1)
     assert build.MSYM_ARGS == {"mode": "basis", "k0": 24, "piece": 16, "npre": 16, "ahead": 1, "anchors": 1}
 
 

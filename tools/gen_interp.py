@@ -158,6 +158,50 @@ def _orbits(nv, perms):
     return orbs
 
 
+def adapted_basis(name, nv, perms, opts):
+    """Symmetry-adapted slot basis: an invertible 0/1 change of basis of the variables, block by block over the orbits
+    of the whole swap group:
+        orbit {v}                    -> v
+        orbit {v1, v2}               -> v1 + v2,  v2
+        orbit {w11, w12, w21, w22}   -> sum of all four,  w21 + w22,  w12 + w22,  w22
+    (`opts`: per block kind "2" = as written, "1" = keep the members with index 1 instead, "none" = leave the block alone;
+    kind = (orbit size, site kinds), see `kind`).  A node's linear form sum_v c_v x_v is rewritten in this basis -- the
+    inverse has entries 0, +-1, the new coefficients are sums / differences of the old ones -- so leaves that are symmetric
+    under a swap collapse onto the sum rows: the saving of the orbit-sum phases for ALL swaps at once, in one phase and in
+    the same registers; a lone leaf on a "first" member costs up to four slots instead of one.  Every row has a distinct
+    lowest variable (its register slot).  -> rows (sorted member lists)"""
+    sites, _ = _sites(name)
+
+    def hidx(v):
+        return tuple(t[-1] if t[0] in "HX" else "0" for t in sites[v])
+
+    def kind(o):
+        p, q = sites[o[0]]
+        return (len(o), tuple(sorted(t[0] + ("i" if p[1] == q[1] else "x") for t in (p, q))))
+    rows = []
+    for o in _orbits(nv, perms):
+        opt = opts.get(kind(o), "none") if len(o) > 1 else "none"
+        if opt == "none":
+            rows += [[v] for v in o]
+        elif len(o) == 2:
+            rows += [o, [max(o, key=hidx) if opt == "2" else min(o, key=hidx)]]
+        else:
+            assert len(o) == 4
+            ids = {v: hidx(v) for v in o}
+            a, b = [q for q in range(2) if len({ids[v][q] for v in o}) == 2]
+            rows += [o, [v for v in o if ids[v][a] == opt], [v for v in o if ids[v][b] == opt],
+                     [v for v in o if ids[v][a] == opt and ids[v][b] == opt]]
+    rows = [sorted(r) for r in rows]
+    assert len(rows) == nv and len({r[0] for r in rows}) == nv
+    return rows
+
+
+# measured best orientation per block kind (tools/gen_interp.py --basis; all 3^k combinations were counted)
+BASIS_OPTS = {"pip2b": {(2, ("Hx", "Ox")): "2", (2, ("Ox", "Xx")): "2", (4, ("Hx", "Xx")): "2", (4, ("Xx", "Xx")): "2"},
+              "pip3b": {(2, ("Hi", "Oi")): "2", (2, ("Hx", "Ox")): "2", (4, ("Hx", "Hx")): "2"}}
+# ("1" rows share their lowest variable with the sum row: usable by gen_msym.py, whose slots are numbered, not here)
+
+
 def _popcount(a):
     a = a.copy()
     c = np.zeros(a.shape, dtype=np.int64)
@@ -182,7 +226,7 @@ def merge_library(req, K):
     return sets
 
 
-def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
+def serialise(name, tab, K, skeleton_weight=40, dual_max=0, basis=False):
     """-> (records, masks, phases, dual).  records: (opcode, k, payload doubles); masks: handler slot tuples; phases: list
     of orbit lists (phase 0 = identity); dual: handler ids that have a DUAL record type, in opcode order."""
     nv = int(tab["n_vars"])
@@ -239,6 +283,22 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
     used = sorted(allowed, key=lambda S: (len(S), S))
     pidx = {S: i for i, S in enumerate(used)}
     phases = [orbs[S] for S in used]
+    if basis:       # ONE phase in the symmetry-adapted basis (adapted_basis): need = {slot: coefficient VALUE}
+        rows = adapted_basis(name, nv, perms, BASIS_OPTS[name])
+        B = np.zeros((nv, nv))
+        for q, m in enumerate(rows):
+            B[q, m] = 1.0
+        BinvT = np.rint(np.linalg.inv(B)).T
+        assert np.array_equal(BinvT.T @ B, np.eye(nv))
+        cls = {}
+        for node, _ in nodes:
+            if node.leaves:
+                c = np.zeros(nv)
+                for v, ci in node.leaves.items():
+                    c[v] = coef[ci]
+                cp = BinvT @ c
+                cls[id(node)] = ((), {rows[q][0]: float(cp[q]) for q in range(nv) if cp[q] != 0.0})
+        used, pidx, phases = [()], {(): 0}, [rows]
     bits = lambda need: sum(1 << j for j in need)  # noqa: E731
     req = collections.Counter(bits(need) for _, need in cls.values())
     lib = merge_library(req, K)
@@ -267,7 +327,7 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0):
 
     def payload(node):
         need = cls[id(node)][1]
-        return [coef[need[j]] if j in need else 0.0 for j in masks[hid[pick[bits(need)]]]]
+        return [(need[j] if basis else coef[need[j]]) if j in need else 0.0 for j in masks[hid[pick[bits(need)]]]]
 
     def emit(node, depth, p):
         assert depth <= MAX_DEPTH
@@ -376,6 +436,8 @@ def interpret(name, words, x, chunk_bytes, masks, phases, dual=()):
     x = np.asarray(x, dtype=np.float64)
     g = np.zeros(nv)                       # the shared-memory accumulators (all of dE/dx at the end)
     xr, gr = x.copy(), np.zeros(nv)        # register slots: orbit sums / orbit gradients of the current phase
+    for o in phases[0]:
+        xr[o[0]] = sum(x[i] for i in o)
     f = words.view(np.float64)
     nm = len(masks)
     t_base = OP_MASK + 2 * nm
@@ -531,6 +593,9 @@ def kernel_ptx(name, entry, stream, masks, nv, phases, dual, block=256, min_bloc
     for i in range(nv):
         w(f"st.shared.f64 [%sx+{i * NT * 8}], %x{i}; st.shared.f64 [%sg+{i * NT * 8}], 0d0000000000000000;")
         w(f"mov.f64 %g{i}, 0d0000000000000000;")
+    for o in phases[0]:                           # (basis mode: phase 0 is not the identity; a thread reads its own column)
+        for i in o[1:]:
+            w(f"ld.shared.f64 %w, [%sx+{i * NT * 8}]; add.rn.f64 %x{o[0]}, %x{o[0]}, %w;")
     w("mov.f64 %vc, 0d0000000000000000; mov.f64 %vd, 0d0000000000000000; mov.f64 %ac, %one;")
     w("bar.sync 0;")
     w("add.u32 %sp, %bufcur, 8;")
@@ -858,13 +923,13 @@ def count_fp64(recs, masks, phases, dual):
 
 
 def generate(name, out_dir, block=256, min_blocks=1, piece=64, sym=32, skeleton_weight=40, fall=4, npre=8, fall_copies=2,
-             dual_max=0, group=4, maxnreg=0, slim=False, anchors=False):
+             dual_max=0, group=4, maxnreg=0, slim=False, anchors=False, basis=False):
     """Write {name}_eval.ptx and {name}_meta.json.  Returns (meta, words, masks, phases, dual)."""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
     assert nv == NV[name]
     chunk = block * piece
-    recs, masks, phases, dual = serialise(name, tab, sym, skeleton_weight, dual_max)
+    recs, masks, phases, dual = serialise(name, tab, sym, skeleton_weight, dual_max, basis)
     nm = len(masks)
     runs = collections.Counter(a[0] for a, b in zip(recs, recs[1:]) if a[0] == b[0])
     lo, hi = OP_MASK + nm, OP_MASK + 2 * nm
@@ -908,6 +973,7 @@ def main():
         ap.add_argument(f"--maxnreg{two}", type=int, default=0, help="register cap (0: none); see kernel_ptx")
         ap.add_argument(f"--slim{two}", type=int, default=0, help="1: saved tree levels keep 2 doubles instead of 4")
         ap.add_argument(f"--anchors{two}", type=int, default=0, help="1: uniform anchors in the rare handlers (see tail())")
+        ap.add_argument(f"--basis{two}", type=int, default=0, help="1: one phase in the symmetry-adapted basis (adapted_basis)")
     ap.add_argument("--skeleton-weight", type=int, default=40)
     ap.add_argument("--fall", type=int, default=4, help="duplicate leaf handlers that follow themselves at least N times")
     ap.add_argument("--fall-copies", type=int, default=2)
@@ -921,7 +987,8 @@ def main():
         meta, *_ = generate(name, args.out, getattr(args, "block" + t), args.min_blocks, getattr(args, "piece" + t),
                             getattr(args, "sym" + t), args.skeleton_weight, args.fall, getattr(args, "npre" + t),
                             args.fall_copies, getattr(args, "dual" + t), args.group, getattr(args, "maxnreg" + t),
-                            bool(getattr(args, "slim" + t)), bool(getattr(args, "anchors" + t)))
+                            bool(getattr(args, "slim" + t)), bool(getattr(args, "anchors" + t)),
+                            bool(getattr(args, "basis" + t)))
         print({k: v for k, v in meta.items() if k != "phases"})
 
 

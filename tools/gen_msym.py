@@ -197,30 +197,8 @@ def adapted_basis(name, nv, swaps, keep="2"):
     contexts; a lone leaf on a "first" member costs up to four slots instead of one.  3B: 4,166 slots instead of 5,326
     (all orientations of the three block types were tried: 4,166 ... 5,452).
     The register of a slot holds the sum of its members; its gradient is added to every member at the end."""
-    sites, _ = gi._sites(name)
-
-    def hidx(v):
-        return tuple(t[-1] if t[0] in "HX" else "0" for t in sites[v])
-    rows = []
-    for o in gi._orbits(nv, swaps):
-        if len(o) == 1:
-            rows.append(o)
-        elif len(o) == 2:
-            (p1, q1) = sites[o[0]]
-            if p1[1] != q1[1]:                           # sites of two molecules: O-H between molecules
-                rows += [[o[0]], [o[1]]]
-            else:
-                rows += [o, [max(o, key=hidx) if keep == "2" else min(o, key=hidx)]]
-        else:
-            assert len(o) == 4
-            ids = {v: hidx(v) for v in o}
-            moving = [q for q in range(2) if len({ids[v][q] for v in o}) == 2]
-            assert len(moving) == 2
-            a, b = moving
-            rows += [o, [v for v in o if ids[v][a] == keep], [v for v in o if ids[v][b] == keep],
-                     [v for v in o if ids[v][a] == keep and ids[v][b] == keep]]
-    assert len(rows) == nv
-    return [(q, sorted(m)) for q, m in enumerate(rows)]
+    rows = gi.adapted_basis(name, nv, swaps, {(2, ("Hi", "Oi")): keep, (4, ("Hx", "Hx")): keep})
+    return [(q, m) for q, m in enumerate(rows)]
 
 
 def symmetrise(name, mode="single"):
