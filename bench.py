@@ -40,10 +40,10 @@ sys.path.insert(0, ROOT)
 
 FLOP2, FLOP3 = 30601, 111818
 # dram__bytes_read.sum + dram__bytes_write.sum of one pip3b_eval launch inside this benchmark (7,103,084 trimers):
-# profiles/r01_ncu_pip3b_eval_final_details.txt
-NCU_DRAM_BYTES_PER_TRIMER = (2.054317e9 + 2.056927e9) / 7103084
-NCU_DRAM_SOURCE = ("ncu --set full (profiles/r01_ncu_pip3b_eval_final_details.txt): 579 B per trimer (algorithmic 584 B), "
-                   "scaled by the trimers of this launch")
+# profiles/r02_ncu_pip3b_eval_msym_details.txt (re-captured for the round-2 kernel: 2.054507 GB read + 2.059910 GB written)
+NCU_DRAM_BYTES_PER_TRIMER = (2.054507e9 + 2.059910e9) / 7103084
+NCU_DRAM_SOURCE = ("ncu --set full of the shipped kernel inside bench.py (profiles/r02_ncu_pip3b_eval_msym_details.txt): "
+                   "579 B per trimer (algorithmic 584 B), scaled by the trimers of this launch")
 NOMINAL_FP64_TF = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
