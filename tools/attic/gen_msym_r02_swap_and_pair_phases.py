@@ -1,4 +1,9 @@
-"""Code generator, second generation: MOLECULE-SYMMETRISED adjoint-Horner evaluator (command stream + sm_100a PTX kernel).
+"""ATTIC (round 2, measured and rejected): gen_msym.py with its two multi-phase modes,
+    --mode swap  : nodes invariant under hydrogen swap a as orbit sums, contexts {e, (bc)} x 3 passes      (2.19 ms vs 1.72)
+    --mode pairs : a second phase whose 36 registers hold the 21 swap pair sums + 15 singles, 6 contexts   (1.91 ms vs 1.72)
+(profiles/r02_microbench_msym_variants.log).  The shipped generator keeps `single` and `basis`.
+
+Code generator, second generation: MOLECULE-SYMMETRISED adjoint-Horner evaluator (command stream + sm_100a PTX kernel).
 
 What tools/gen_interp.py (round 1 / 2) does per tuple and where it stops.  One thread evaluates one tuple; every leaf
 coefficient of the Horner tree is a warp-uniform double that has to reach the FMA through a vector register: one
@@ -20,10 +25,10 @@ built by the greedy Horner split WITH IMAGE FREEDOM: an orbit may follow any of 
 the most popular prefixes (3B: 365 leaf nodes / 5,326 slots for 5,657 orbits instead of 610 / 5,121 with fixed
 lexicographic representatives).
 
-Hydrogen swaps.  The orbit-sum saving of gen_interp.py's symmetry phases is obtained in ONE phase through the symmetry-adapted
-slot basis (`adapted_basis`, --mode basis): a register holds the sum of a row of variables, the node's linear form is
-rewritten in that basis when the stream is generated.  (Two multi-phase variants -- swap-a orbit sums with two contexts in
-three passes, and a pair-sum phase -- were measured and rejected: tools/attic/gen_msym_r02_swap_and_pair_phases.py.)
+Swap phases.  Nodes whose leaf coefficients are constant on the orbits of a hydrogen swap are linear forms in orbit sums
+(gen_interp.py, symmetry phases).  With molecule contexts only the contexts that normalise the swap can share the orbit-sum
+registers (3B, swap a: e and (bc)); the other cosets are separate PASSES over the same nodes with the registers loaded in
+permuted order.  A phase is therefore (swap set S, pass permutation tau, context list), see `Phase`.
 
 Records (all carry the opcode of their successor in the header, like gen_interp.py):
     LEAF_h   k[C], c0, coefs : for every context c:  a' = a_c x_{k_c};  u = c0 + sum_j coef_j R_{pi_c(j)};
@@ -171,6 +176,19 @@ class Phase:
         self.kmap = [compose(tau, rho) for rho in ctx]
 
 
+PAIR_SINGLES = {"pip3b": [21, 23, 25, 27, 29, 31, 22, 24, 26, 28, 30, 32, 33, 34, 35]}     # O-H and O-O between molecules
+
+
+def pair_slots(name, nv, swaps):
+    """the mixed family of `pairs` mode: the 21 hydrogen-swap pair sums x_v + x_swap(v) of all three swaps (closed under
+    the molecule relabellings, so ALL six contexts can use them) + the singles that leaf nodes with pairs need most,
+    filling the same 36 registers"""
+    pairs = sorted({tuple(sorted((v, s[v]))) for s in swaps for v in range(nv) if s[v] != v})
+    members = [list(p) for p in pairs] + [[v] for v in PAIR_SINGLES[name]]
+    assert len(members) <= nv
+    return [(q, m) for q, m in enumerate(members)]
+
+
 def adapted_basis(name, nv, swaps, keep="2"):
     """Symmetry-adapted slot family of `basis` mode: an invertible 0/1 change of basis of the nv variables, block by block
     over the orbits of the hydrogen-swap group, closed under the molecule relabellings:
@@ -188,19 +206,24 @@ def adapted_basis(name, nv, swaps, keep="2"):
     return [(q, m) for q, m in enumerate(rows)]
 
 
-def symmetrise(name, mode="basis"):
+def symmetrise(name, mode="single"):
     """-> (root of the tree of Q, nv, phases, molecule permutations).
-    mode single : 36 single-variable slots;  basis (shipped) : the symmetry-adapted slot basis (`adapted_basis`).
-    One phase, all molecule relabellings as contexts."""
+    mode single: one phase, 36 single-variable slots, all molecule permutations as contexts.
+         swap  : + class 1 = orbit sums of swap a, contexts e and (bc), three passes (measured: slower; kept for the record)
+         pairs : + class 1 = pair sums of all swaps + 15 singles, all contexts (see pair_slots)"""
     tab = dict(np.load(os.path.join(DATA, name + ".npz")))
     nv = int(tab["n_vars"])
     coef = tab["coef"]
     monos = {tuple(sorted(int(v) for v in row if v != PAD)): int(c) for row, c in zip(tab["mono_vars"], tab["mono_coef"])}
-    perms = list(mol_perms(name).values())
+    mp = mol_perms(name)
+    perms = list(mp.values())
     for p in perms:                                     # the premise: invariance under every molecule relabelling
         assert all(monos.get(img(p, m)) == c for m, c in monos.items())
     swaps = gi.swap_perms(name)
-    root = build_free(s_orbits(monos, coef, perms), None, lambda v: 0)
+    sites, _ = gi._sites(name)
+    ha = [any(s.startswith("Ha") for s in p) for p in sites]
+    orbs = s_orbits(monos, coef, perms)
+    root = build_free(orbs, None, (lambda v: 0 if ha[v] else 1) if mode == "swap" else (lambda v: 0))
     # exactness of the representation: sum over the images of Q == P, term by term
     acc = collections.defaultdict(float)
     for m, val in expand(root).items():
@@ -210,32 +233,84 @@ def symmetrise(name, mode="basis"):
     assert max(abs(acc[m] - coef[c]) / abs(coef[c]) for m, c in monos.items()) < 1e-15
     ident = list(range(nv))
     if mode.startswith("basis"):
-        slots = adapted_basis(name, nv, swaps, mode[5:] or "2")
+        phases = [Phase(nv, adapted_basis(name, nv, swaps, mode[5:] or "2"), ident, perms, 0)]
+        return root, nv, phases, perms
+    phases = [Phase(nv, [(v, [v]) for v in range(nv)], ident, perms, 0)]
+    if mode == "swap":
+        assert name == "pip3b"
+        bc, ab, ac = mp[("a", "c", "b")], mp[("b", "a", "c")], mp[("c", "b", "a")]
+        slots = [(o[0], o) for o in gi._orbits(nv, [swaps[0]])]
+        for tau in (ident, ab, ac):
+            phases.append(Phase(nv, slots, tau, [ident, bc], 1))
+        cover = sorted(tuple(compose(ph.tau, rho)) for ph in phases[1:] for rho in ph.ctx)
+        assert cover == sorted(tuple(p) for p in perms)
+    elif mode == "pairs":
+        phases.append(Phase(nv, pair_slots(name, nv, swaps), ident, perms, 1))
     else:
         assert mode == "single"
-        slots = [(v, [v]) for v in range(nv)]
-    return root, nv, [Phase(nv, slots, ident, perms, 0)], perms
+    return root, nv, phases, perms
 
 
-def classify(root, phases, mode):
-    """-> {id(node): [(class, need = {slot: value}, constant or None)]} for every node with leaves or a constant: the
-    node's linear form in the slot basis of the (one) phase"""
-    ph = phases[0]
-    nv = len(ph.sid)
-    B = np.zeros((nv, nv))
-    for q, m in zip(ph.sid, ph.orbs):
-        B[q, m] = 1.0
-    BinvT = np.rint(np.linalg.inv(B)).T                # entries 0, +-1: sum_v c_v x_v = sum_q (B^-T c)_q (B x)_q
-    assert np.array_equal(BinvT.T @ B, np.eye(nv))
+def classify(root, phases, mode, overhead=3):
+    """-> {id(node): [(class, need = {slot: value}, constant or None), ...]} for every node with leaves or a constant.
+    single: everything in class 0.  swap: the class that needs fewest slots.  pairs: a node is evaluated in class 0, in
+    class 1 or SPLIT between them (its linear form is a sum of two), whatever costs least with `overhead` slots per record."""
+    by_cls = {}
+    for ph in phases:
+        by_cls.setdefault(ph.cls, ph)
     out = {}
+
+    def express(n, ph):
+        """greedy cover of the leaves with the slots of ph: pair slots where both members carry the same coefficient,
+        single slots otherwise; -> (need, leaves left over)"""
+        left, need = dict(n.leaves), {}
+        for j, m in zip(ph.sid, ph.orbs):
+            if len(m) > 1 and all(v in left for v in m) and len({left[v] for v in m}) == 1:
+                need[j] = left[m[0]]
+                for v in m:
+                    del left[v]
+        for j, m in zip(ph.sid, ph.orbs):
+            if len(m) == 1 and m[0] in left:
+                need[j] = left.pop(m[0])
+        return need, left
+
+    if mode.startswith("basis"):
+        ph = by_cls[0]
+        nv = len(ph.sid)
+        B = np.zeros((nv, nv))
+        for q, m in zip(ph.sid, ph.orbs):
+            B[q, m] = 1.0
+        BinvT = np.rint(np.linalg.inv(B)).T                # entries 0, +-1: sum_v c_v x_v = sum_q (B^-T c)_q (B x)_q
+        assert np.array_equal(BinvT.T @ B, np.eye(nv))
 
     def walk(n):
         if n.leaves or n.const is not None:
-            c = np.zeros(nv)
-            for v, val in n.leaves.items():
-                c[v] = val
-            cp = BinvT @ c
-            out[id(n)] = [(0, {q: float(cp[q]) for q in range(nv) if cp[q] != 0.0}, n.const)]
+            full = {v: c for v, c in n.leaves.items()}
+            if mode.startswith("basis"):
+                c = np.zeros(nv)
+                for v, val in n.leaves.items():
+                    c[v] = val
+                cp = BinvT @ c
+                out[id(n)] = [(0, {q: float(cp[q]) for q in range(nv) if cp[q] != 0.0}, n.const)]
+            elif mode == "single":
+                out[id(n)] = [(0, full, n.const)]
+            elif mode == "swap":
+                best = (0, full)
+                need, left = express(n, by_cls[1])
+                if not left and len(need) < len(full):
+                    best = (1, need)
+                out[id(n)] = [(best[0], best[1], n.const)]
+            else:
+                need, left = express(n, by_cls[1])
+                c0 = len(full) + overhead
+                c1 = len(need) + overhead if not left else 1 << 30
+                c2 = len(need) + len(left) + 2 * overhead if need and left else 1 << 30
+                if c0 <= min(c1, c2):
+                    out[id(n)] = [(0, full, n.const)]
+                elif c1 <= c2:
+                    out[id(n)] = [(1, need, n.const)]
+                else:
+                    out[id(n)] = [(1, need, n.const), (0, left, None)]
         for k in n.kids:
             walk(k)
     walk(root)
@@ -250,11 +325,11 @@ def op_layout(phases, handlers=()):
     return ncls, op_trans, op_leaf0, op_leaf0 + len(handlers)
 
 
-def serialise(name, K=(24,), mode="basis"):
+def serialise(name, K=(12, 12), mode="single", overhead=3):
     """-> (records, handlers, phases, nv).  records: (op, [node variable per context], payload doubles, [parent's node
     variables: LEAVE_2 only]); handlers: list of (class, slot tuple) in opcode order (LEAF_h = op_leaf0 + h)."""
     root, nv, phases, perms = symmetrise(name, mode)
-    cls = classify(root, phases, mode)
+    cls = classify(root, phases, mode, overhead)
     ncls, op_trans, op_leaf0, _ = op_layout(phases)
     bits = lambda need: sum(1 << j for j in need)  # noqa: E731
     libs, pick = [], []
@@ -792,8 +867,9 @@ def count_fp64(recs, handlers, phases):
     return n_fp, hist
 
 
-def generate(name, out_dir, block=256, piece=16, K=(24,), npre=16, mode="basis", ahead=1, maxnreg=0, anchors=True):
-    recs, handlers, phases, nv = serialise(name, K, mode)
+def generate(name, out_dir, block=256, piece=64, K=(12, 12), npre=8, mode="single", ahead=2, maxnreg=0, anchors=False,
+             overhead=3):
+    recs, handlers, phases, nv = serialise(name, K, mode, overhead)
     cmax = max(len(ph.ctx) for ph in phases)
     chunk = block * piece
     kvars = node_vars(recs)
@@ -826,16 +902,18 @@ def main():
     ap.add_argument("--out", default=GEN)
     ap.add_argument("--only", default="pip3b")
     ap.add_argument("--block", type=int, default=256)
-    ap.add_argument("--piece", type=int, default=16, help="stream bytes each thread stages per chunk")
-    ap.add_argument("--k0", type=int, default=24, help="size of the leaf-handler library")
-    ap.add_argument("--npre", type=int, default=16, help="payload words of the next record every handler pre-loads")
-    ap.add_argument("--ahead", type=int, default=1, help="in-body coefficient loads issued this many word pairs ahead")
-    ap.add_argument("--mode", default="basis", help="single | basis (see symmetrise)")
+    ap.add_argument("--piece", type=int, default=64)
+    ap.add_argument("--k0", type=int, default=12, help="leaf handlers of class 0 (no swap)")
+    ap.add_argument("--k1", type=int, default=12, help="leaf handlers of class 1 (swap phase)")
+    ap.add_argument("--npre", type=int, default=8)
+    ap.add_argument("--ahead", type=int, default=2)
+    ap.add_argument("--mode", default="single", help="single | swap | pairs (see symmetrise)")
+    ap.add_argument("--overhead", type=int, default=3, help="pairs mode: cost of a record in slots (node split decision)")
     ap.add_argument("--maxnreg", type=int, default=0)
-    ap.add_argument("--anchors", type=int, default=1, help="uniform anchors: BRXU dispatch")
+    ap.add_argument("--anchors", type=int, default=0)
     args = ap.parse_args()
-    meta, *_ = generate(args.only, args.out, args.block, args.piece, (args.k0,), args.npre, args.mode,
-                        args.ahead, args.maxnreg, bool(args.anchors))
+    meta, *_ = generate(args.only, args.out, args.block, args.piece, (args.k0, args.k1), args.npre, args.mode,
+                        args.ahead, args.maxnreg, bool(args.anchors), args.overhead)
     print(meta)
 
 

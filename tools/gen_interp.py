@@ -168,8 +168,8 @@ def adapted_basis(name, nv, perms, opts):
     kind = (orbit size, site kinds), see `kind`).  A node's linear form sum_v c_v x_v is rewritten in this basis -- the
     inverse has entries 0, +-1, the new coefficients are sums / differences of the old ones -- so leaves that are symmetric
     under a swap collapse onto the sum rows: the saving of the orbit-sum phases for ALL swaps at once, in one phase and in
-    the same registers; a lone leaf on a "first" member costs up to four slots instead of one.  Every row has a distinct
-    lowest variable (its register slot).  -> rows (sorted member lists)"""
+    the same registers; a lone leaf on a "first" member costs up to four slots instead of one.
+    -> rows (sorted member lists; with the "2" orientation every row has a distinct lowest variable)"""
     sites, _ = _sites(name)
 
     def hidx(v):
@@ -192,7 +192,7 @@ def adapted_basis(name, nv, perms, opts):
             rows += [o, [v for v in o if ids[v][a] == opt], [v for v in o if ids[v][b] == opt],
                      [v for v in o if ids[v][a] == opt and ids[v][b] == opt]]
     rows = [sorted(r) for r in rows]
-    assert len(rows) == nv and len({r[0] for r in rows}) == nv
+    assert len(rows) == nv
     return rows
 
 
@@ -285,6 +285,7 @@ def serialise(name, tab, K, skeleton_weight=40, dual_max=0, basis=False):
     phases = [orbs[S] for S in used]
     if basis:       # ONE phase in the symmetry-adapted basis (adapted_basis): need = {slot: coefficient VALUE}
         rows = adapted_basis(name, nv, perms, BASIS_OPTS[name])
+        assert len({r[0] for r in rows}) == nv           # a row's register slot = its lowest variable: must be distinct
         B = np.zeros((nv, nv))
         for q, m in enumerate(rows):
             B[q, m] = 1.0
