@@ -93,6 +93,37 @@ def test_bare_polynomial(order):
     assert np.abs(grad - g["g" + k]).max() <= 1e-12 * np.abs(g["g" + k]).max()
 
 
+@pytest.mark.parametrize("order,n", [(2, 1), (2, 385), (2, 1000), (3, 1), (3, 257), (3, 1000)])
+def test_bare_polynomial_ragged_batches_and_relabelling(order, n):
+    """the generated evaluators on batches that do not fill their last CTA (384 / 256 tuples per CTA), against the monomial
+    tables on the CPU; and the symmetry the 3B evaluator is built on: relabelling the molecules permutes the variables, the
+    energy must not move and the gradient must move with the variables (tools/gen_msym.py evaluates the six relabellings
+    of every trimer as six contexts of one thread)"""
+    import os
+    import sys
+    import torch
+    from conftest import ROOT
+    from mbpol_openmm_plugin_b200 import pip_eval
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import extract_pip
+    import gen_msym
+    name = {2: "pip2b", 3: "pip3b"}[order]
+    t = dict(np.load(os.path.join(ROOT, "mbpol_openmm_plugin_b200", "data", name + ".npz")))
+    nv = int(t["n_vars"])
+    x = np.random.default_rng(100 * order + n).uniform(0.05, 1.5, (nv, n))
+    e, g = pip_eval(order, torch.as_tensor(x).cuda())
+    e, g = e.cpu().numpy(), g.cpu().numpy()
+    for i in sorted({0, n // 2, n - 1}):
+        er, gr = extract_pip.eval_table(t, x[:, i])
+        assert abs(e[i] - er) <= 1e-12 * max(1.0, abs(er))
+        assert np.abs(g[:, i] - gr).max() <= 1e-12 * np.abs(gr).max()
+    for pm in list(gen_msym.mol_perms(name).values())[1:]:
+        pm = np.asarray(pm)
+        ep, gp = pip_eval(order, torch.as_tensor(np.ascontiguousarray(x[pm])).cuda())
+        assert np.abs(ep.cpu().numpy() - e).max() <= 1e-12 * max(1.0, np.abs(e).max())
+        assert np.abs(gp.cpu().numpy() - g[pm]).max() <= 1e-12 * np.abs(g).max()
+
+
 @pytest.mark.parametrize("case", ["water14_nocut", "water256_bulk"])
 def test_per_tuple_parity(case, checker):
     """energy and 6x3 / 9x3 force block of every single tuple against the oracle (before any summation)"""
