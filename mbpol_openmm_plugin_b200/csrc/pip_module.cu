@@ -1,7 +1,7 @@
 // Polynomial stage: the generated sm_100a kernels pip2b_eval / pip3b_eval.
 //
 // The two PIP evaluators (replacing poly_2b_v6x_eval, platforms/reference/src/poly-2b-v6x.cpp:3-13841, and
-// poly_3b_v2x::eval, poly-3b-v2x.cpp:3-28378) are emitted as PTX by tools/gen_horner.py, assembled to cubins by ptxas
+// poly_3b_v2x::eval, poly-3b-v2x.cpp:3-28378) are emitted as PTX by tools/gen_interp.py (2B) and tools/gen_msym.py (3B), assembled to cubins by ptxas
 // at build time and embedded here as byte arrays (gen/pip_cubins.inc).  They are loaded with the driver API, obtained
 // through cudaGetDriverEntryPoint so that the library has no link-time dependency on libcuda (it must be loadable, for
 // symbol checks, on a machine without a GPU driver).
