@@ -35,8 +35,12 @@ std::string check_indices(const int32_t* idx, int64_t n_mol, int64_t n_particles
 }
 double eff_cutoff(int method, double c) { return method == MBPOL_NOCUTOFF ? 1e10 : c; }
 
-// One body order over the owned tuple range.  order = 2 | 3.
-int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool first_into_fmol) {
+// One body order over the owned tuple range.  order = 2 | 3.  part: ALL, or the chain split in two so that two orders can
+// be enqueued on two streams -- COMPUTE (variables, polynomial, per-tuple force blocks, contribution index) and REDUCE
+// (segmented force reduction into f_mol, energy sum).  side: the chain uses the second set of scratch buffers.
+enum { PART_ALL = 0, PART_COMPUTE = 1, PART_REDUCE = 2 };
+int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool first_into_fmol, int part = PART_ALL,
+              bool side = false) {
     TupleLists& L = ctx->lists;
     const int width = order;
     const int nv = order == 2 ? NV2 : NV3;
@@ -57,6 +61,7 @@ int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool
     for (int d = 0; d < 3; ++d) box.len[d] = ctx->box[d];
     box.periodic = is_periodic(order == 2 ? ctx->method2 : ctx->method3);
     const int32_t* idx = ctx->idx.as<int32_t>();
+    if (part == PART_REDUCE) goto reduce;
     if (order == 2) {
         launch_dimer_vars(pos, idx, tuples, first, n, ld, box, X.as<double>(), s);
         if (ctx->timing) cudaEventRecord(ctx->evp[0], s);
@@ -70,11 +75,17 @@ int run_order(mbpol_ctx* ctx, int order, const double* pos, cudaStream_t s, bool
         if (ctx->timing) cudaEventRecord(ctx->evp[3], s);
         launch_trimer_forces(pos, idx, tuples, first, n, ld, box, O.as<double>(), E.as<double>(), F.as<double>(), s);
     }
-    if ((rc = ci.build(tuples, width, first, n, ctx->n_mol, L.cub_tmp, s, err))) return rc;
+    if ((rc = ci.build(tuples, width, first, n, ctx->n_mol, side ? ctx->cub_tmp2 : L.cub_tmp, s, err))) return rc;
+    if (part == PART_COMPUTE) goto done;
+reduce:
     launch_force_reduce(ci, width, F.as<double>(), ctx->n_mol, ctx->f_mol.as<double>(), !first_into_fmol, s);
-    launch_energy_sum(E.as<double>(), n, ctx->e_partial.as<double>(), ctx->d_energy.as<double>() + (order - 2), s);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, MBPOL_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    launch_energy_sum(E.as<double>(), n, (side ? ctx->e_partial2 : ctx->e_partial).as<double>(),
+                      ctx->d_energy.as<double>() + (order - 2), s);
+done:
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, MBPOL_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    }
     return MBPOL_OK;
 }
 
@@ -130,6 +141,27 @@ int eval_pass(mbpol_ctx* ctx, const double* pos, bool want2, bool want3, bool pe
     }
     r_lists.end();
     if (ctx->timing) cudaEventRecord(ctx->ev[1], s);
+    if (want2 && want3 && !ctx->timing && !ctx->serial_orders && ctx->side) {
+        // Two chains, two streams.  Issue order = priority of the block scheduler: the 3B chain first (its polynomial
+        // kernel takes every SM, wave after wave), the 2B chain on `side` fills the SMs that the last, partial 3B wave
+        // leaves idle, and the small kernels of either chain run next to the other's polynomial kernel.  f_mol keeps its
+        // order of additions (2B written first, 3B added): the 3B reduction waits for the 2B chain.
+        NvtxRange r("mbpol:2B||3B");
+        const bool first = !fmol_started;
+        if (cudaEventRecord(ctx->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0) != cudaSuccess)
+            return fail(ctx, MBPOL_ECUDA, "two-stream fork failed");
+        if ((rc = run_order(ctx, 3, pos, s, false, PART_COMPUTE))) return rc;
+        if ((rc = run_order(ctx, 2, pos, ctx->side, first, PART_ALL, true))) return rc;
+        if (cudaEventRecord(ctx->ev_join, ctx->side) != cudaSuccess || cudaStreamWaitEvent(s, ctx->ev_join, 0) != cudaSuccess)
+            return fail(ctx, MBPOL_ECUDA, "two-stream join failed");
+        if ((rc = run_order(ctx, 3, pos, s, false, PART_REDUCE))) return rc;
+        fmol_started = true;
+        want2 = want3 = false;                               // (the counters below still need the flags: restored there)
+        ctx->stats.n_pairs = ctx->lists.sliced ? -1 : ctx->lists.n_pairs;
+        ctx->stats.n_pairs_owned = ctx->lists.own_p1 - ctx->lists.own_p0;
+        ctx->stats.n_triplets = ctx->lists.sliced ? -1 : ctx->lists.n_trips;
+        ctx->stats.n_triplets_owned = ctx->lists.own_t1 - ctx->lists.own_t0;
+    }
     if (want2) {
         NvtxRange r("mbpol:2B");
         if ((rc = run_order(ctx, 2, pos, s, !fmol_started))) return rc;
@@ -216,6 +248,12 @@ int mbpol_create(mbpol_ctx** out, const mbpol_config* cfg) {
     cudaMemset(ctx->d_energy.ptr, 0, 4 * sizeof(double));
     if (const char* f = getenv("MBPOL_FORCE_TWO_PASS")) ctx->lists.force_two_pass = f[0] == '1';
     if (const char* f = getenv("MBPOL_REPARTITION_EVERY")) ctx->repartition_every = atoi(f);   // 0: never slice
+    if (const char* f = getenv("MBPOL_SERIAL_ORDERS")) ctx->serial_orders = f[0] == '1';
+    if (ctx->e_partial2.reserve(sizeof(double) * 1024, err)) return bail(MBPOL_ENOMEM, err);
+    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(MBPOL_ECUDA, "creating the side stream failed");
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->evp) cudaEventCreate(&e);
     for (auto& e : ctx->evc) cudaEventCreate(&e);
@@ -230,6 +268,9 @@ void mbpol_destroy(mbpol_ctx* ctx) {
     for (auto* set : {ctx->ev + 0, ctx->evp + 0, ctx->evc + 0})
         for (int i = 0; i < (set == ctx->ev ? 6 : 4); ++i)
             if (set[i]) cudaEventDestroy(set[i]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
 }
 

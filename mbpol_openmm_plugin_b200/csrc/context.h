@@ -39,6 +39,13 @@ struct mbpol_ctx {
     bool timing_defer_sync = false;           // the caller reads the stage events itself (mbpol_collect_timing)
     bool timed2 = false, timed3 = false;
     bool f_mol_valid = false;
+    // Two body orders on two streams (capi.cu, eval_pass): the 2B chain runs on `side` next to the 3B chain on the caller's
+    // stream, so that the partial last wave of one polynomial kernel and the small kernels around it overlap the other
+    // chain.  Only when the stage events are off (they describe a serial schedule); MBPOL_SERIAL_ORDERS=1 disables it.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DeviceBuf cub_tmp2, e_partial2;           // scratch of the chain on `side`
+    bool serial_orders = false;
     // multi-GPU (dist.cu)
     void* comm = nullptr;                     // ncclComm_t
     bool comm_owned = false;
