@@ -327,10 +327,8 @@ def main():
             ctx.setForceOutput(f_host.numpy())
             ctx.calcForcesAndEnergy()
         else:
-            _, force = nf.step(pos_host if rank == 0 else None)              # pinned host -> device -> broadcast
-            if rank == 0:
-                f_host.copy_(force, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+            # pinned host -> device -> broadcast -> slices -> reduce in four parts, each copied back as soon as it is done
+            nf.step_host(pos_host if rank == 0 else None, f_host if rank == 0 else None)
 
     # ---- parity of the N-GPU path against ONE unpartitioned context on the same positions (rank 0), before timing
     parity = None
@@ -348,8 +346,13 @@ def main():
                       "bars": {"rel_dE": 1e-9, "max_abs_dF_kJ_mol_nm": 1e-6},
                       "against": "one unpartitioned context, same positions, same GPU as rank 0"}
             parity["ok"] = bool(parity["rel_dE2"] <= 1e-9 and parity["rel_dE3"] <= 1e-9 and parity["max_abs_dF"] <= 1e-6)
-            del f1
             one.engine.close()
+        # ... and the host-buffer path (mbpol_eval_distributed_host: sliced reduce + overlapped copy-back) against it
+        step_e2e()
+        if rank == 0:
+            parity["max_abs_dF_host_path"] = float((f_host.to(dev) - f1).abs().max().item())
+            parity["ok"] = bool(parity["ok"] and parity["max_abs_dF_host_path"] <= 1e-6)
+            del f1
         ok = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
         dist.broadcast(ok, src=0)
         if not int(ok.item()):

@@ -193,6 +193,14 @@ int  mbpol_comm_destroy(mbpol_ctx* ctx);
 int  mbpol_eval_distributed(mbpol_ctx* ctx, double* pos_nm, double* force, double* energy, uint32_t flags,
                             void* stream);
 
+/* The same with HOST buffers on rank 0 (the Reference-platform calling convention, extractPositions / extractForces,
+ * MBPolReferenceKernels.cpp:51-61, for a multi-GPU run): pos_host (rank 0: n_particles x 3, ideally pinned) goes to the
+ * device and is broadcast; the forces are reduced to rank 0 in four slices and every slice starts its way back to
+ * force_host (rank 0, OVERWRITTEN) on a copy stream as soon as its reduce is done, so the device-to-host transfer hides
+ * behind the remaining reduces.  Other ranks pass NULL for both.  Returns after the results are in host memory. */
+int  mbpol_eval_distributed_host(mbpol_ctx* ctx, const double* pos_host, double* force_host, double* energy,
+                                 uint32_t flags);
+
 /* ---- TT-damped C6 dispersion ------------------------------------------------------------------
  * What python/mbpol.xml:37-108 builds as an OpenMM CustomNonbondedForce: for every pair of O / H atoms of DIFFERENT
  * molecules (M sites excluded) with minimum-image distance r <= cutoff_nm:  E = -C6 tt6(r) / r^6,

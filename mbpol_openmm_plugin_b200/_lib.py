@@ -26,7 +26,7 @@ EXPORTS = (
     "mbpol_get_triplets", "mbpol_get_stats", "mbpol_set_timing", "mbpol_pip_eval", "mbpol_eval_tuples",
     "mbpol_measure_fp64_peak", "mbpol_pip_instruction_count", "mbpol_eval_onebody", "mbpol_eval_onebody_host",
     "mbpol_energy_device", "mbpol_get_energy", "mbpol_eval_openmm", "mbpol_comm_unique_id", "mbpol_comm_init_rank",
-    "mbpol_comm_adopt", "mbpol_comm_destroy", "mbpol_eval_distributed", "mbpol_set_skin", "mbpol_nve_run", "mbpol_eval_dispersion", "mbpol_eval_dispersion_host",
+    "mbpol_comm_adopt", "mbpol_comm_destroy", "mbpol_eval_distributed", "mbpol_eval_distributed_host", "mbpol_set_skin", "mbpol_nve_run", "mbpol_eval_dispersion", "mbpol_eval_dispersion_host",
 )
 
 
@@ -107,6 +107,7 @@ def load():
     L.mbpol_comm_adopt.argtypes = [vp, vp]
     L.mbpol_comm_destroy.argtypes = [vp]
     L.mbpol_eval_distributed.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32, vp]
+    L.mbpol_eval_distributed_host.argtypes = [vp, dp, dp, C.POINTER(C.c_double), C.c_uint32]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("mbpol_destroy", "mbpol_last_error", "mbpol_energy_device"):

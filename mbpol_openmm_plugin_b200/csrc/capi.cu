@@ -271,6 +271,10 @@ void mbpol_destroy(mbpol_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->ev_slice)
+        if (e) cudaEventDestroy(e);
     delete ctx;
 }
 

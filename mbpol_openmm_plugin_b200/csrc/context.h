@@ -50,6 +50,8 @@ struct mbpol_ctx {
     void* comm = nullptr;                     // ncclComm_t
     bool comm_owned = false;
     DeviceBuf dist_buf;                       // partial forces of this rank [3 n_particles] + reduced energies [2]
+    cudaStream_t side2 = nullptr, copy_stream = nullptr;      // mbpol_eval_distributed_host: compute / copy-back streams
+    cudaEvent_t ev_slice[4] = {};
     // OpenMM buffers (omm.cu): original particle -> reordered slot, built by the posq gather
     DeviceBuf omm_slot;
     // Verlet skin (lists.cu) and on-device integrator (nve.cu)

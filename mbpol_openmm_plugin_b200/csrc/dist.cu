@@ -198,4 +198,64 @@ int mbpol_eval_distributed(mbpol_ctx* ctx, double* pos_nm, double* force, double
     return MBPOL_OK;
 }
 
+int mbpol_eval_distributed_host(mbpol_ctx* ctx, const double* pos_host, double* force_host, double* energy, uint32_t flags) {
+    if (!ctx) return MBPOL_EINVAL;
+    if (!ctx->comm) return fail(ctx, MBPOL_EINVAL, "mbpol_eval_distributed_host: no communicator (mbpol_comm_init_rank)");
+    if (ctx->rank == 0 && (!pos_host || !force_host))
+        return fail(ctx, MBPOL_EINVAL, "mbpol_eval_distributed_host: rank 0 needs the host position and force buffers");
+    const NcclApi& N = nccl();
+    if (!N.ok) return fail(ctx, MBPOL_ECOMM, N.why);
+    CKC(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->side2 ? ctx->side2 : nullptr;        // compute / collectives
+    if (!s) {
+        CKC(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
+        CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev_slice) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s = ctx->side2;
+    }
+    const size_t n3 = 3 * (size_t)ctx->n_particles, bytes = sizeof(double) * n3;
+    int rc;
+    if ((rc = ctx->pos_stage.reserve(bytes + 8, ctx->err))) return rc;
+    if ((rc = ctx->force_stage.reserve(bytes + 8, ctx->err))) return rc;
+    if ((rc = ctx->dist_buf.reserve(sizeof(double) * (n3 + 8), ctx->err))) return rc;
+    double* pos = ctx->pos_stage.as<double>();
+    double* part = ctx->dist_buf.as<double>();
+    double* sum = ctx->force_stage.as<double>();
+    if (ctx->rank == 0) CKC(cudaMemcpyAsync(pos, pos_host, bytes, cudaMemcpyHostToDevice, s));
+    {
+        NvtxRange r("mbpol:broadcast");
+        CKN(N.Broadcast(pos, pos, n3, NCCL_FLOAT64, 0, ctx->comm, s));
+    }
+    CKC(cudaMemsetAsync(part, 0, bytes, s));
+    const bool timing = ctx->timing;
+    ctx->timing = false;                                    // the stage events describe mbpol_eval_distributed, not this path
+    rc = mbpol_eval(ctx, pos, part, nullptr, flags & (MBPOL_DO_2B | MBPOL_DO_3B | MBPOL_KEEP_LISTS), s);
+    ctx->timing = timing;
+    if (rc) return rc;
+    NvtxRange r_red("mbpol:reduce+d2h");
+    double* e_sum = part + n3;
+    constexpr int NSLICE = 4;
+    const size_t per = ((n3 + NSLICE - 1) / NSLICE + 1) & ~(size_t)1;
+    for (int c = 0; c < NSLICE; ++c) {
+        const size_t lo = (size_t)c * per, hi = lo + per < n3 ? lo + per : n3;
+        if (lo >= hi) break;
+        CKN(N.GroupStart());
+        CKN(N.Reduce(part + lo, sum + lo, hi - lo, NCCL_FLOAT64, NCCL_SUM, 0, ctx->comm, s));
+        if (c == 0) CKN(N.Reduce(ctx->d_energy.ptr, e_sum, 2, NCCL_FLOAT64, NCCL_SUM, 0, ctx->comm, s));
+        CKN(N.GroupEnd());
+        if (ctx->rank == 0) {
+            CKC(cudaEventRecord(ctx->ev_slice[c], s));
+            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_slice[c], 0));
+            CKC(cudaMemcpyAsync(force_host + lo, sum + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (c == 0 && energy)
+                CKC(cudaMemcpyAsync(energy, e_sum, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    r_red.end();
+    CKC(cudaStreamSynchronize(s));
+    if (ctx->rank == 0) CKC(cudaStreamSynchronize(ctx->copy_stream));
+    CKC(cudaGetLastError());
+    return MBPOL_OK;
+}
+
 }  // extern "C"

@@ -75,6 +75,16 @@ class NcclForce:
                                                  torch.cuda.current_stream().cuda_stream), h)
         return ((self._e[0], self._e[1]) if (want_energy and receiver) else None), self.force
 
+    def step_host(self, pos_host=None, force_host=None, want_energy=True):
+        """host buffers on rank 0 (torch CPU tensors, ideally pinned; None elsewhere): positions in, summed forces out
+        (overwritten).  The reduce is sliced and the device-to-host copy of every slice overlaps the next reduce."""
+        h = self.ctx.engine.h
+        r0 = self.rank == 0
+        _lib.check(self.L.mbpol_eval_distributed_host(h, pos_host.data_ptr() if r0 else None,
+                                                      force_host.data_ptr() if r0 else None,
+                                                      self._e if (want_energy and r0) else None, self.flags & 3), h)
+        return (self._e[0], self._e[1]) if (want_energy and r0) else None
+
     def close(self):
         if self.ctx is not None:
             self.L.mbpol_comm_destroy(self.ctx.engine.h)

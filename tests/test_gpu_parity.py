@@ -695,3 +695,36 @@ def test_sliced_build_that_falls_back_on_some_ranks_keeps_the_owner_ranges():
         assert (f_sum - f_full).abs().max().item() < 1e-8
     assert fallback_seen > 0                                     # the situation of the test did occur
     assert all(c.engine.stats()["n_repartitions"] == 1 for c in ranks)          # nobody rebalanced on its own
+
+
+def test_distributed_entry_points_on_a_single_rank_communicator():
+    """mbpol_eval_distributed and mbpol_eval_distributed_host (device / host buffers, NCCL broadcast + reduce, the sliced
+    reduce with overlapped copy-back) on a communicator of ONE rank must reproduce mbpol_eval bit for bit -- the
+    collectives are identities there, everything else is the code path the N-GPU runs take (bench.py checks N > 1)."""
+    import ctypes as C
+    import torch
+    from mbpol_openmm_plugin_b200 import _lib
+    g = load_golden("water256_bulk")
+    n = len(g["pos_mol"])
+    ctx = make_context(n, g["box"], True)
+    L = _lib.load()
+    h = ctx.engine.h
+    pos = torch.as_tensor(g["pos_mol"].reshape(-1, 3)).cuda()
+    f0 = torch.zeros_like(pos)
+    e0 = ctx.engine.eval_device(pos, f0, 3)
+    ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    _lib.check(L.mbpol_comm_unique_id(ident))
+    _lib.check(L.mbpol_comm_init_rank(h, ident.raw, 0, 1), h)
+    try:
+        f1 = torch.full_like(pos, 7.0)                       # overwritten, not accumulated into
+        e1 = (C.c_double * 2)()
+        _lib.check(L.mbpol_eval_distributed(h, pos.data_ptr(), f1.data_ptr(), e1, 3, None), h)
+        torch.cuda.synchronize()
+        assert (e1[0], e1[1]) == tuple(e0) and torch.equal(f1, f0)
+        ph = torch.as_tensor(g["pos_mol"].reshape(-1, 3)).pin_memory()
+        fh = torch.full((3 * n, 3), -1.0, dtype=torch.float64).pin_memory()
+        e2 = (C.c_double * 2)()
+        _lib.check(L.mbpol_eval_distributed_host(h, ph.data_ptr(), fh.data_ptr(), e2, 3), h)
+        assert (e2[0], e2[1]) == tuple(e0) and torch.equal(fh, f0.cpu())
+    finally:
+        L.mbpol_comm_destroy(h)
