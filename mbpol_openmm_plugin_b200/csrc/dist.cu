@@ -113,7 +113,19 @@ int mbpol_comm_init_rank(mbpol_ctx* ctx, const void* id_bytes, int32_t rank, int
     NcclUniqueId id;
     memcpy(id.internal, id_bytes, MBPOL_COMM_ID_BYTES);
     NcclComm comm = nullptr;
-    CKN(N.CommInitRank(&comm, world, id, rank));
+    // This communicator carries two messages per step: 3 n_particles doubles out (broadcast) and back (reduce), 19 MB at
+    // 262,144 waters.  NCCL's cost model picks the Simple protocol for them; measured on 8 B200 over NVSwitch the reduce
+    // then takes 0.25 ms, with LL128 0.06 ms (profiles/r02_nccl_proto_8gpu.txt; between two ranks Simple is the faster
+    // one, 0.12 against 0.16 ms, so the default is only changed from four ranks on).  NCCL reads NCCL_PROTO when a
+    // communicator is tuned, so it is set for the duration of THIS init only -- unless the user set it, or asks for
+    // something else through MBPOL_NCCL_PROTO (empty string: leave NCCL alone).
+    const char* want = getenv("MBPOL_NCCL_PROTO");
+    if (!want) want = "LL128";
+    const bool set_proto = !getenv("NCCL_PROTO") && want[0] != 0 && (world >= 4 || getenv("MBPOL_NCCL_PROTO"));
+    if (set_proto) setenv("NCCL_PROTO", want, 1);
+    const int init_rc = N.CommInitRank(&comm, world, id, rank);
+    if (set_proto) unsetenv("NCCL_PROTO");
+    CKN(init_rc);
     ctx->comm = comm;
     ctx->comm_owned = true;
     return mbpol_set_partition(ctx, rank, world);
